@@ -1,0 +1,157 @@
+/*
+ * celltree_b200.h -- C-ABI of libcelltree_b200.so, the sm_100a implementation of the
+ * numba_celltree query hot path.
+ *
+ * The reference (Deltares/numba_celltree, pure Python + Numba) has no FFI layer; its seam is
+ * "API class method -> module-level @njit array function" (SURVEY.md section 8b).  Every entry
+ * point below replaces one or more of those array functions; the replaced reference interface is
+ * cited as file:line (paths relative to the reference's numba_celltree/ package).  The host-side
+ * Python classes in numba_celltree_b200/ bind these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all functions return 0 on success, a CT_ERR_* code otherwise
+ *     (ct_last_error() gives the message for the calling thread).
+ *   - `mem` says where EVERY array argument of that call lives: CT_MEM_HOST (NumPy buffers; the
+ *     call does the host<->device copies) or CT_MEM_DEVICE (pointers into this process' CUDA
+ *     context, e.g. torch tensors; no PCIe traffic).  Outputs are written to caller-owned buffers.
+ *   - calls are synchronous with respect to the host for CT_MEM_HOST.  For CT_MEM_DEVICE the work
+ *     is enqueued on the stream set with ct_set_stream() (default: the legacy default stream) and
+ *     only entry points that must return a size (variable-length results) synchronise.
+ *   - integer arrays are int64 (np.intp, constants.py:27), floats are float64, C-contiguous.
+ *   - box rows are (xmin, xmax, ymin, ymax); edge rows are ((x0, y0), (x1, y1)).
+ */
+#ifndef CELLTREE_B200_H
+#define CELLTREE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CT_OK 0
+#define CT_ERR_CUDA 1          /* CUDA runtime error (no device, out of memory, launch failure) */
+#define CT_ERR_VALUE 2         /* invalid argument (maps to Python ValueError) */
+#define CT_ERR_UNBUCKETABLE 3  /* tree build: an element's centroid falls in no bucket (reference: IndexError, creation.py:130-131) */
+#define CT_ERR_DEPTH 4         /* tree deeper than the compiled traversal stack capacity */
+#define CT_ERR_CLIP_STATE 5    /* "Undefined clipping state" (cohen_sutherland.py:86) */
+
+#define CT_MEM_HOST 0
+#define CT_MEM_DEVICE 1
+
+#define CT_KIND_FACES 0 /* CellTree2d: elements are polygons of <= 32 vertices, -1 filled */
+#define CT_KIND_EDGES 1 /* EdgeCellTree2d: elements are 2-vertex segments */
+
+typedef struct ct_tree ct_tree;     /* device-resident cell tree (opaque) */
+typedef struct ct_result ct_result; /* device-resident variable-length result (opaque) */
+
+/* Byte-exact image of one row of the reference's NodeDType (constants.py:91-106), 41 bytes. */
+#pragma pack(push, 1)
+typedef struct ct_node41 {
+    int64_t child; /* index of left child; right child is child + 1; -1 for a leaf */
+    double Lmax;
+    double Rmin;
+    int64_t ptr;   /* into bb_indices */
+    int64_t size;
+    uint8_t dim;   /* 0 = x, 1 = y */
+} ct_node41;
+#pragma pack(pop)
+
+typedef struct ct_tree_info {
+    int64_t n_vertex;
+    int64_t n_elem;
+    int64_t n_nodes;
+    int32_t n_max_vert;
+    int32_t kind;
+    int32_t n_buckets;
+    int32_t cells_per_leaf;
+    int32_t depth;            /* number of node levels (root alone = 1) */
+    int32_t reserved;
+    double bbox[4];           /* bbox_tree(), celltree_base.py:20-25 */
+    double default_tolerance; /* default_tolerance(bb_distances[:, 2]), celltree_base.py:51-52 */
+    double build_ms;          /* device time of the build (CUDA events) */
+} ct_tree_info;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char *ct_last_error(void);
+int ct_device_count(int *count);
+int ct_set_device(int device);
+/* cudaStream_t as void*; applies to subsequent calls of the calling thread. NULL = legacy default stream. */
+int ct_set_stream(void *cuda_stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t ct_launch_count(void);
+
+/* ---- construction --------------------------------------------------------------------------
+ * ct_tree_create replaces the constructor pipeline of CellTree2d.__init__ (celltree.py:74-97) /
+ * EdgeCellTree2d.__init__ (edge_celltree.py:57-83):
+ *   counter_clockwise      geometry_utils.py:541-561   (faces only; the corrected faces are kept)
+ *   build_face_bboxes      geometry_utils.py:443-456   / build_edge_bboxes :473-487
+ *   creation.initialize    creation.py:384-413         (nodes and bb_indices bit-exact)
+ *   bbox_tree, bbox_distances, default_tolerance       celltree_base.py:20-52
+ * elements: (n_elem, n_max_vert) int64, FILL_VALUE (-1) padded (cast_faces already applied).
+ * edge_tolerance: the bounding-box padding for CT_KIND_EDGES (edge_celltree.py:59-64); ignored for faces.
+ */
+int ct_tree_create(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem,
+                   int32_t n_max_vert, int32_t kind, int32_t n_buckets, int32_t cells_per_leaf,
+                   double edge_tolerance, int32_t mem, ct_tree **out);
+
+/* Upload a tree that was built elsewhere (arrays as the reference's CellTreeData holds them,
+ * constants.py:82-89): no build kernels run. `elements` are used as given (no counter_clockwise). */
+int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem,
+                        int32_t n_max_vert, int32_t kind, const ct_node41 *nodes, int64_t n_nodes,
+                        const int64_t *bb_indices, const double *bb_coords, int32_t cells_per_leaf,
+                        int32_t mem, ct_tree **out);
+
+int ct_tree_get_info(const ct_tree *tree, ct_tree_info *info);
+
+/* Host/device mirrors of the tree attributes (celltree.py:80-97). Any pointer may be NULL (skipped).
+ * nodes: n_nodes x 41 bytes; bb_indices: n_elem; bb_coords: n_elem x 4; elements: n_elem x n_max_vert
+ * (after counter_clockwise); bb_distances: n_elem x 3 (dx, dy, diagonal). */
+int ct_tree_download(const ct_tree *tree, ct_node41 *nodes, int64_t *bb_indices, double *bb_coords,
+                     int64_t *elements, double *bb_distances, int32_t mem);
+
+void ct_tree_destroy(ct_tree *tree);
+
+/* ---- fixed-size queries ---------------------------------------------------------------------
+ * ct_locate_points replaces query.locate_points (query.py:110-117) for CT_KIND_FACES and
+ * query.locate_points_on_edge (query.py:168-174) for CT_KIND_EDGES.
+ * If weights != NULL (faces only) it also replaces barycentric_triangle_weights
+ * (algorithms/barycentric_triangle.py:46-64, n_max_vert == 3) / barycentric_wachspress_weights
+ * (algorithms/barycentric_wachspress.py:88-107, n_max_vert > 3): weights is (n, n_max_vert).
+ * points: (n, 2); out_index: n (-1 = not found).
+ */
+int ct_locate_points(const ct_tree *tree, const double *points, int64_t n, double tolerance,
+                     int64_t *out_index, double *weights, int32_t mem);
+
+/* ---- variable-length queries: count -> scan -> fill on the device, then fetch ---------------
+ * ct_locate_boxes replaces query.locate_boxes (query.py:278-289); with with_area != 0 it also runs
+ * algorithms.box_area_of_intersection (sutherland_hodgman.py:171-187) and keeps area > 0
+ * (celltree.py:174-184): the payload is then one double per pair (the area).
+ */
+int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t n, int32_t with_area, int32_t mem,
+                    ct_result **out);
+
+/* ct_locate_faces replaces CellTree2d.locate_faces' kernels (celltree.py:212-226): counter_clockwise on
+ * the QUERY faces (in place: `faces` is rewritten, as the reference does), build_face_bboxes,
+ * locate_boxes, polygons_intersect (separating_axis.py:58-75).  With with_area != 0 it continues with
+ * area_of_intersection (sutherland_hodgman.py:151-168) and keeps area > 0 (celltree.py:258-269). */
+int ct_locate_faces(const ct_tree *tree, const double *vertices, int64_t n_vertex, int64_t *faces,
+                    int64_t n_face, int32_t n_max_vert, int32_t with_area, int32_t mem, ct_result **out);
+
+/* ct_intersect_edges replaces query.locate_edge_faces (query.py:542-544, CT_KIND_FACES) /
+ * query.locate_edge_edges (query.py:537-539, CT_KIND_EDGES) followed by
+ * geometry_utils.sort_intersections_by_edge (geometry_utils.py:564-574).
+ * Payload per pair: 4 doubles ((cx, cy), (dx, dy)). */
+int ct_intersect_edges(const ct_tree *tree, const double *edges, int64_t n, int32_t mem, ct_result **out);
+
+int64_t ct_result_size(const ct_result *result);
+int32_t ct_result_payload_width(const ct_result *result); /* doubles per pair: 0, 1 or 4 */
+/* Copy out the pairs: i = query index, j = tree element index (both int64), payload may be NULL. */
+int ct_result_fetch(const ct_result *result, int64_t *i, int64_t *j, double *payload, int32_t mem);
+void ct_result_free(ct_result *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLTREE_B200_H */

@@ -1,0 +1,110 @@
+"""
+ctypes binding of libcelltree_b200.so (include/celltree_b200.h).
+
+There is no fallback: if the CUDA library is missing or no GPU is usable the calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+
+HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = HERE / "libcelltree_b200.so"
+
+CT_OK = 0
+CT_ERR_CUDA = 1
+CT_ERR_VALUE = 2
+CT_ERR_UNBUCKETABLE = 3
+CT_ERR_DEPTH = 4
+CT_ERR_CLIP_STATE = 5
+CT_MEM_HOST = 0
+CT_MEM_DEVICE = 1
+CT_KIND_FACES = 0
+CT_KIND_EDGES = 1
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_f64 = ctypes.c_double
+c_void_p = ctypes.c_void_p
+
+
+class TreeInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_vertex", c_i64),
+        ("n_elem", c_i64),
+        ("n_nodes", c_i64),
+        ("n_max_vert", c_i32),
+        ("kind", c_i32),
+        ("n_buckets", c_i32),
+        ("cells_per_leaf", c_i32),
+        ("depth", c_i32),
+        ("reserved", c_i32),
+        ("bbox", c_f64 * 4),
+        ("default_tolerance", c_f64),
+        ("build_ms", c_f64),
+    ]
+
+
+_SIGNATURES = {
+    "ct_last_error": (ctypes.c_char_p, []),
+    "ct_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "ct_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "ct_set_stream": (ctypes.c_int, [c_void_p]),
+    "ct_launch_count": (c_i64, []),
+    "ct_tree_create": (
+        ctypes.c_int,
+        [c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_i32, ctypes.POINTER(c_void_p)],
+    ),
+    "ct_tree_from_arrays": (
+        ctypes.c_int,
+        [c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_void_p, c_i64, c_void_p, c_void_p, c_i32, c_i32, ctypes.POINTER(c_void_p)],
+    ),
+    "ct_tree_get_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(TreeInfo)]),
+    "ct_tree_download": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_tree_destroy": (None, [c_void_p]),
+    "ct_locate_points": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_f64, c_void_p, c_void_p, c_i32]),
+    "ct_locate_boxes": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, ctypes.POINTER(c_void_p)]),
+    "ct_locate_faces": (
+        ctypes.c_int,
+        [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_void_p)],
+    ),
+    "ct_intersect_edges": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, ctypes.POINTER(c_void_p)]),
+    "ct_result_size": (c_i64, [c_void_p]),
+    "ct_result_payload_width": (c_i32, [c_void_p]),
+    "ct_result_fetch": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_result_free": (None, [c_void_p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m numba_celltree_b200.build_ext` "
+                "(nvcc, sm_100a). numba_celltree_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == CT_OK:
+        return
+    message = load().ct_last_error().decode("utf-8", "replace")
+    if status == CT_ERR_VALUE:
+        raise ValueError(message)
+    if status == CT_ERR_UNBUCKETABLE:
+        raise IndexError(message)
+    raise RuntimeError(f"libcelltree_b200 error {status}: {message}")

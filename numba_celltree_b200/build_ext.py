@@ -1,0 +1,64 @@
+"""
+Compile libcelltree_b200.so in-tree with nvcc for sm_100a.
+
+    python -m numba_celltree_b200.build_ext [--force]
+
+Flags that matter for parity: -fmad=false (the reference's Numba/LLVM code has no fused multiply-adds;
+bucket membership, on-edge decisions and pair lists depend on the last bit).  fp64 division and sqrt are
+IEEE-correct on the GPU by default.  -lineinfo keeps the ncu source page usable.
+"""
+
+from __future__ import annotations
+
+import pathlib
+import subprocess
+import sys
+
+HERE = pathlib.Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libcelltree_b200.so"
+SOURCES = [CSRC / "query.cu", CSRC / "build.cu"]
+HEADERS = [CSRC / "common.cuh", CSRC / "geometry.cuh", CSRC / "traverse.cuh", HERE.parent / "include" / "celltree_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "--expt-relaxed-constexpr",
+    "-cudart", "static",
+]  # fmt: skip
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = CSRC / (src.stem + ".o")
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}")
+    link = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+    subprocess.run(link, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1149 @@
+// build.cu -- mesh preparation and level-synchronous cell tree construction on the GPU.
+//
+// Replaces the serial constructor pipeline of the reference (celltree.py:74-97):
+//   counter_clockwise (geometry_utils.py:541-561), build_face_bboxes / build_edge_bboxes (:443-487),
+//   creation.initialize / build (creation.py:233-413), bbox_tree / bbox_distances / default_tolerance
+//   (celltree_base.py:20-52).
+//
+// The reference builds depth-first with an explicit stack; every node only permutes its own slice
+// [ptr, ptr + size) of bb_indices, so the result is independent of the processing order EXCEPT for the node
+// numbering.  Here all nodes of one "wave" are processed together, element-parallel:
+//
+//   k_range    per element: min of box-min / max of box-max of its node in the node's dim   (get_bounds, :153-171)
+//   k_bucket   per element: bucket of the bbox centroid (first bucket whose [Min, Max) holds it, :44-51, :278-293)
+//              + per (node, bucket) count, Rmin, Lmax                                      (:301-306)
+//   k_decide   per node: special case cells_per_leaf == 1 (:312-320), drop empty buckets (:322-341), retry in the
+//              other dim / oversized leaf (:345-358), split_plane (:174-213), create the two children (:365-379)
+//   scan+k_rank+k_scatter  stable partition of each node's slice by bucket (sort_bbox_indices / stable_partition,
+//              :54-150): new position = ptr + (elements in lower buckets) + (rank among same-bucket elements)
+//
+// and afterwards the nodes are renumbered to the reference's numbering: the k-th SPLITTING node in left-first
+// pre-order owns children 1 + 2k and 2 + 2k (:373-379).  Subtree split counts bottom-up, pre-order ranks
+// top-down, one kernel per wave each.
+//
+// min / max over doubles use atomicMin / atomicMax on an order-preserving uint64 image of the double.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <cstring>
+#include <vector>
+
+#include "geometry.cuh"
+
+namespace ct {
+
+constexpr int BB = 256;
+
+// ---- ordered image of a double ---------------------------------------------------------------------------
+CT_DEV unsigned long long enc(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+CT_DEV double dec(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+    return __longlong_as_double((long long)u);
+}
+static inline unsigned long long enc_host(double d) {
+    unsigned long long u;
+    memcpy(&u, &d, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+static inline double dec_host(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+// ---- small conversion kernels ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(BB) k_widen(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+    int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (k < n) out[k] = in[k];
+}
+__global__ void __launch_bounds__(BB) k_narrow(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+    int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (k < n) out[k] = (int32_t)in[k];
+}
+int launch_widen(const int32_t *in, int64_t n, int64_t *out, cudaStream_t s) {
+    if (n <= 0) return CT_OK;
+    k_widen<<<grid_for(n, BB), BB, 0, s>>>(in, n, out);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s) {
+    if (n <= 0) return CT_OK;
+    k_narrow<<<grid_for(n, BB), BB, 0, s>>>(in, n, out);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+// ---- counter_clockwise, geometry_utils.py:541-561 ----------------------------------------------------------
+// Literal restatement: a stateful loop, NOT a signed-area test -- after a flip the loop carries on with the
+// stale a, b, exactly as the reference does.
+__global__ void __launch_bounds__(BB) k_counter_clockwise(const double2 *__restrict__ vertices, int32_t *__restrict__ faces,
+                                                          int64_t n_face, int M) {
+    int64_t f = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (f >= n_face) return;
+    int32_t *face = faces + f * M;
+    int length = M;  // polygon_length, :72-79
+    for (int i = 3; i < M; i++)
+        if (face[i] == -1) {
+            length = i;
+            break;
+        }
+    double2 a2 = vertices[face[length - 2]], b2 = vertices[face[length - 1]];
+    P2 a{a2.x, a2.y}, b{b2.x, b2.y};
+    for (int i = 0; i < length; i++) {
+        double2 c2 = vertices[face[i]];
+        P2 c{c2.x, c2.y};
+        P2 u = to_vector(a, b);
+        P2 v = to_vector(a, c);
+        double product = cross_product(u, v);
+        if (product == 0) {
+            a = b;
+            b = c;
+        } else if (product < 0) {
+            int end = length - 1;  // flip, :532-538
+            for (int k = 0; k < length / 2; k++) {
+                int32_t t = face[k];
+                face[k] = face[end - k];
+                face[end - k] = t;
+            }
+        } else {
+            break;
+        }
+    }
+}
+int launch_counter_clockwise(const double2 *vertices, int32_t *faces, int64_t n_face, int M, cudaStream_t s) {
+    if (n_face <= 0) return CT_OK;
+    k_counter_clockwise<<<grid_for(n_face, BB), BB, 0, s>>>(vertices, faces, n_face, M);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+// ---- build_face_bboxes / bounding_box, geometry_utils.py:421-456 ----------------------------------------
+__global__ void __launch_bounds__(BB) k_face_bboxes(const double2 *__restrict__ vertices, const int32_t *__restrict__ faces,
+                                                    int64_t n_face, int M, double *__restrict__ bb) {
+    int64_t f = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (f >= n_face) return;
+    const int32_t *face = faces + f * M;
+    double2 first = vertices[face[0]];
+    double xmin = first.x, xmax = first.x, ymin = first.y, ymax = first.y;
+    for (int k = 1; k < M; k++) {
+        int index = face[k];
+        if (index == -1) break;
+        double2 v = vertices[index];
+        xmin = nb_min(xmin, v.x);
+        xmax = nb_max(xmax, v.x);
+        ymin = nb_min(ymin, v.y);
+        ymax = nb_max(ymax, v.y);
+    }
+    double2 *o = reinterpret_cast<double2 *>(bb + 4 * f);
+    o[0] = make_double2(xmin, xmax);
+    o[1] = make_double2(ymin, ymax);
+}
+int launch_face_bboxes(const double2 *vertices, const int32_t *faces, int64_t n_face, int M, double *bb, cudaStream_t s) {
+    if (n_face <= 0) return CT_OK;
+    k_face_bboxes<<<grid_for(n_face, BB), BB, 0, s>>>(vertices, faces, n_face, M, bb);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+// ---- build_edge_bboxes / edge_bounding_box, geometry_utils.py:459-487 ----------------------------------
+__global__ void __launch_bounds__(BB) k_edge_bboxes(const double2 *__restrict__ vertices, const int32_t *__restrict__ edges,
+                                                    int64_t n_edge, double tolerance, double *__restrict__ bb) {
+    int64_t e = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (e >= n_edge) return;
+    double2 v0 = vertices[edges[2 * e]], v1 = vertices[edges[2 * e + 1]];
+    double2 *o = reinterpret_cast<double2 *>(bb + 4 * e);
+    o[0] = make_double2(nb_min(v0.x - tolerance, v1.x - tolerance), nb_max(v0.x + tolerance, v1.x + tolerance));
+    o[1] = make_double2(nb_min(v0.y - tolerance, v1.y - tolerance), nb_max(v0.y + tolerance, v1.y + tolerance));
+}
+
+// ---- bbox_tree + max bbox diagonal, celltree_base.py:20-52 --------------------------------------------
+// red[0..3] = enc(min xmin), enc(max xmax), enc(min ymin), enc(max ymax); red[4] = enc(max diagonal)
+__global__ void __launch_bounds__(BB) k_bbox_reduce(const double *__restrict__ bb, int64_t n, unsigned long long *__restrict__ red) {
+    double xmin = FLOAT_MAX, xmax = FLOAT_MIN, ymin = FLOAT_MAX, ymax = FLOAT_MIN, diag = FLOAT_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x; i < n; i += (int64_t)gridDim.x * BB) {
+        Box4 b = load_box(bb, i);
+        xmin = b.xmin < xmin ? b.xmin : xmin;
+        xmax = b.xmax > xmax ? b.xmax : xmax;
+        ymin = b.ymin < ymin ? b.ymin : ymin;
+        ymax = b.ymax > ymax ? b.ymax : ymax;
+        double dx = b.xmax - b.xmin, dy = b.ymax - b.ymin;
+        double d = sqrt(dx * dx + dy * dy);  // bbox_distances, celltree_base.py:41-47
+        diag = d > diag ? d : diag;
+    }
+    unsigned long long e0 = enc(xmin), e1 = enc(xmax), e2 = enc(ymin), e3 = enc(ymax), e4 = enc(diag);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t;
+        t = __shfl_xor_sync(0xffffffffu, e0, o); e0 = t < e0 ? t : e0;
+        t = __shfl_xor_sync(0xffffffffu, e1, o); e1 = t > e1 ? t : e1;
+        t = __shfl_xor_sync(0xffffffffu, e2, o); e2 = t < e2 ? t : e2;
+        t = __shfl_xor_sync(0xffffffffu, e3, o); e3 = t > e3 ? t : e3;
+        t = __shfl_xor_sync(0xffffffffu, e4, o); e4 = t > e4 ? t : e4;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(red + 0, e0);
+        atomicMax(red + 1, e1);
+        atomicMin(red + 2, e2);
+        atomicMax(red + 3, e3);
+        atomicMax(red + 4, e4);
+    }
+}
+
+__global__ void __launch_bounds__(BB) k_bb_distances(const double *__restrict__ bb, int64_t n, double *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n) return;
+    Box4 b = load_box(bb, i);
+    double dx = b.xmax - b.xmin, dy = b.ymax - b.ymin;
+    out[3 * i] = dx;
+    out[3 * i + 1] = dy;
+    out[3 * i + 2] = sqrt(dx * dx + dy * dy);
+}
+
+// ---- NodeDType (41 bytes, packed) <-> Node32 -----------------------------------------------------------------
+// A block converts 256 nodes; the packed side is staged through shared memory so that global traffic is
+// coalesced 4-byte words (256 * 41 bytes is a multiple of 4).
+constexpr int NODE41 = 41;
+
+__global__ void __launch_bounds__(BB) k_pack_nodes(const Node32 *__restrict__ nodes, int64_t n, unsigned char *__restrict__ out) {
+    __shared__ __align__(16) unsigned char buf[BB * NODE41];
+    int64_t base = (int64_t)blockIdx.x * BB;
+    int64_t i = base + threadIdx.x;
+    if (i < n) {
+        Node32 nd = nodes[i];
+        ct_node41 p;
+        p.child = nd.child;
+        p.Lmax = nd.Lmax;
+        p.Rmin = nd.Rmin;
+        p.ptr = nd.ptr;
+        p.size = nd.size;
+        p.dim = (uint8_t)(nd.dim ? 1 : 0);
+        memcpy(buf + threadIdx.x * NODE41, &p, NODE41);
+    }
+    __syncthreads();
+    int64_t count = (n - base) < BB ? (n - base) : BB;
+    int64_t bytes = count * NODE41;
+    unsigned char *dst = out + base * NODE41;  // base * 41 is a multiple of 4
+    int64_t words = bytes / 4;
+    for (int64_t w = threadIdx.x; w < words; w += BB) reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<uint32_t *>(buf)[w];
+    for (int64_t b = words * 4 + threadIdx.x; b < bytes; b += BB) dst[b] = buf[b];
+}
+
+__global__ void __launch_bounds__(BB) k_unpack_nodes(const unsigned char *__restrict__ in, int64_t n, Node32 *__restrict__ nodes) {
+    __shared__ __align__(16) unsigned char buf[BB * NODE41];
+    int64_t base = (int64_t)blockIdx.x * BB;
+    int64_t count = (n - base) < BB ? (n - base) : BB;
+    int64_t bytes = count * NODE41;
+    const unsigned char *src = in + base * NODE41;
+    int64_t words = bytes / 4;
+    for (int64_t w = threadIdx.x; w < words; w += BB) reinterpret_cast<uint32_t *>(buf)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+    for (int64_t b = words * 4 + threadIdx.x; b < bytes; b += BB) buf[b] = src[b];
+    __syncthreads();
+    int64_t i = base + threadIdx.x;
+    if (i < n) {
+        ct_node41 p;
+        memcpy(&p, buf + threadIdx.x * NODE41, NODE41);
+        Node32 nd;
+        nd.child = (int32_t)p.child;
+        nd.Lmax = p.Lmax;
+        nd.Rmin = p.Rmin;
+        nd.ptr = (int32_t)p.ptr;
+        nd.size = (int32_t)p.size;
+        nd.dim = p.dim ? 1 : 0;
+        nodes[i] = nd;
+    }
+}
+
+// depth of an uploaded tree: parent links, then every node counts its ancestors
+__global__ void __launch_bounds__(BB) k_parents(const Node32 *__restrict__ nodes, int64_t n, int32_t *__restrict__ parent) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n) return;
+    int c = nodes[i].child;
+    if (c >= 0 && c + 1 < n) {
+        parent[c] = (int32_t)i;
+        parent[c + 1] = (int32_t)i;
+    }
+}
+__global__ void __launch_bounds__(BB) k_depth(const int32_t *__restrict__ parent, int64_t n, int32_t *__restrict__ max_depth) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n) return;
+    int d = 1;
+    int p = parent[i];
+    while (p >= 0 && d < (1 << 20)) {
+        d++;
+        p = parent[p];
+    }
+    atomicMax(max_depth, d);
+}
+
+// ==============================================================================================================
+// Level-synchronous build
+// ==============================================================================================================
+struct BuildState {
+    // elements
+    const double *bb;
+    int32_t *seg;  // slot of the active node that owns this position, -1 when the position is final
+    uint8_t *bkt;  // bucket of the element at this position (valid where seg >= 0)
+    // nodes in creation order
+    int32_t *n_ptr, *n_size, *n_child;
+    uint8_t *n_dim, *n_tried;
+    double *n_Lmax, *n_Rmin;
+    // per active slot
+    const int32_t *active;
+    unsigned long long *a_min, *a_max;
+    int32_t *b_cnt;                    // [slot * nb + k]
+    unsigned long long *b_min, *b_max;  // [slot * nb + k]
+    int32_t *b_start;                  // [slot * nb + k] exclusive prefix of b_cnt
+    int32_t *next_left, *next_right, *split_pos;
+    int32_t *next_active;
+    int32_t *counters;  // [0] node count, [1] next active count, [2] error flag
+    int nb, cpl;
+};
+
+__global__ void __launch_bounds__(BB) k_init_slots(BuildState st, int n_active) {
+    int s = blockIdx.x * BB + threadIdx.x;
+    if (s >= n_active) return;
+    st.a_min[s] = enc(FLOAT_MAX);   // get_bounds starts from FLOAT_MAX / FLOAT_MIN, creation.py:161-162
+    st.a_max[s] = enc(FLOAT_MIN);
+    for (int k = 0; k < st.nb; k++) {
+        st.b_cnt[(int64_t)s * st.nb + k] = 0;
+        st.b_min[(int64_t)s * st.nb + k] = enc(FLOAT_MAX);
+        st.b_max[(int64_t)s * st.nb + k] = enc(FLOAT_MIN);
+    }
+}
+
+// get_bounds over a node's slice (creation.py:153-171).  `value < Rmin` / `value > Lmax` never pick a NaN.
+__global__ void __launch_bounds__(BB) k_range(BuildState st, const int32_t *__restrict__ idx, int64_t n) {
+    __shared__ unsigned long long s_min[BB / 32], s_max[BB / 32];
+    int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    int64_t first = (int64_t)blockIdx.x * BB;
+    int64_t last = first + BB - 1 < n - 1 ? first + BB - 1 : n - 1;
+    int slot_first = st.seg[first], slot_last = st.seg[last];
+    // a node's positions are contiguous: equal slots at both ends of the block => one node owns the block
+    bool uniform = (slot_first == slot_last) && slot_first >= 0;
+    int slot = pos < n ? st.seg[pos] : -1;
+    unsigned long long emin = enc(FLOAT_MAX), emax = enc(FLOAT_MIN);
+    if (slot >= 0) {
+        int node = st.active[slot];
+        int dim = st.n_dim[node];
+        int e = idx[pos];
+        double vmin = st.bb[4 * (int64_t)e + 2 * dim];
+        double vmax = st.bb[4 * (int64_t)e + 2 * dim + 1];
+        if (vmin == vmin) emin = enc(vmin);
+        if (vmax == vmax) emax = enc(vmax);
+    }
+    if (!uniform) {
+        if (slot >= 0) {
+            atomicMin(st.a_min + slot, emin);
+            atomicMax(st.a_max + slot, emax);
+        }
+        return;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t;
+        t = __shfl_xor_sync(0xffffffffu, emin, o); emin = t < emin ? t : emin;
+        t = __shfl_xor_sync(0xffffffffu, emax, o); emax = t > emax ? t : emax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = emin;
+        s_max[threadIdx.x >> 5] = emax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < BB / 32; w++) {
+            emin = s_min[w] < emin ? s_min[w] : emin;
+            emax = s_max[w] > emax ? s_max[w] : emax;
+        }
+        atomicMin(st.a_min + slot_first, emin);
+        atomicMax(st.a_max + slot_first, emax);
+    }
+}
+
+constexpr int SMEM_BUCKETS = 64;
+
+// Bucket of every element (centroid_test, creation.py:44-51, applied bucket after bucket by
+// sort_bbox_indices :115-150: the FIRST bucket whose half-open range holds the centroid) and per-bucket
+// count / Rmin / Lmax (get_bounds per bucket, :301-306).
+__global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__restrict__ idx, int64_t n) {
+    __shared__ int s_cnt[SMEM_BUCKETS];
+    __shared__ unsigned long long s_bmin[SMEM_BUCKETS], s_bmax[SMEM_BUCKETS];
+    const int nb = st.nb;
+    int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    int64_t first = (int64_t)blockIdx.x * BB;
+    int64_t last = first + BB - 1 < n - 1 ? first + BB - 1 : n - 1;
+    int slot_first = st.seg[first], slot_last = st.seg[last];
+    bool uniform = (slot_first == slot_last) && slot_first >= 0 && nb <= SMEM_BUCKETS;
+    if (uniform) {
+        for (int k = threadIdx.x; k < nb; k += BB) {
+            s_cnt[k] = 0;
+            s_bmin[k] = enc(FLOAT_MAX);
+            s_bmax[k] = enc(FLOAT_MIN);
+        }
+        __syncthreads();
+    }
+    int slot = pos < n ? st.seg[pos] : -1;
+    if (slot >= 0) {
+        int node = st.active[slot];
+        int dim = st.n_dim[node];
+        int e = idx[pos];
+        double vmin = st.bb[4 * (int64_t)e + 2 * dim];
+        double vmax = st.bb[4 * (int64_t)e + 2 * dim + 1];
+        double range_Rmin = dec(st.a_min[slot]);
+        double range_Lmax = dec(st.a_max[slot]);
+        double bucket_length = (range_Lmax - range_Rmin) / (double)nb;  // creation.py:278
+        double centroid = vmin + 0.5 * (vmax - vmin);                    // creation.py:50
+        int k = -1;
+        for (int b = 0; b < nb; b++) {
+            double bmax = (double)(b + 1) * bucket_length + range_Rmin;  // creation.py:286
+            double bmin = (double)b * bucket_length + range_Rmin;        // creation.py:287
+            if ((centroid >= bmin) && (centroid < bmax)) {
+                k = b;
+                break;
+            }
+        }
+        if (k < 0) {
+            atomicExch(st.counters + 2, CT_ERR_UNBUCKETABLE);
+            k = nb - 1;
+        }
+        st.bkt[pos] = (uint8_t)k;
+        unsigned long long emin = (vmin == vmin) ? enc(vmin) : enc(FLOAT_MAX);
+        unsigned long long emax = (vmax == vmax) ? enc(vmax) : enc(FLOAT_MIN);
+        if (uniform) {
+            atomicAdd(&s_cnt[k], 1);
+            atomicMin(&s_bmin[k], emin);
+            atomicMax(&s_bmax[k], emax);
+        } else {
+            int64_t o = (int64_t)slot * nb + k;
+            atomicAdd(st.b_cnt + o, 1);
+            atomicMin(st.b_min + o, emin);
+            atomicMax(st.b_max + o, emax);
+        }
+    }
+    if (uniform) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nb; k += BB) {
+            if (s_cnt[k] > 0) {
+                int64_t o = (int64_t)slot_first * nb + k;
+                atomicAdd(st.b_cnt + o, s_cnt[k]);
+                atomicMin(st.b_min + o, s_bmin[k]);
+                atomicMax(st.b_max + o, s_bmax[k]);
+            }
+        }
+    }
+}
+
+CT_DEV void make_node(const BuildState &st, int id, int ptr, int size, int dim) {  // create_node, creation.py:27-29
+    st.n_child[id] = -1;
+    st.n_Lmax[id] = -1.0;
+    st.n_Rmin[id] = -1.0;
+    st.n_ptr[id] = ptr;
+    st.n_size[id] = size;
+    st.n_dim[id] = (uint8_t)dim;
+    st.n_tried[id] = 0;
+}
+
+// One thread per active node: everything build() does after the per-bucket bounds (creation.py:308-379).
+__global__ void __launch_bounds__(128) k_decide(BuildState st, int n_active) {
+    int slot = blockIdx.x * 128 + threadIdx.x;
+    if (slot >= n_active) return;
+    const int nb = st.nb;
+    const int node = st.active[slot];
+    const int ptr = st.n_ptr[node], size = st.n_size[node];
+    const int dim = st.n_dim[node];
+    const int64_t o = (int64_t)slot * nb;
+    double range_Rmin = dec(st.a_min[slot]);
+    double range_Lmax = dec(st.a_max[slot]);
+    double bucket_length = (range_Lmax - range_Rmin) / (double)nb;
+
+    // bucket start offsets for the stable partition
+    int run = 0, n_nonempty = 0;
+    for (int k = 0; k < nb; k++) {
+        st.b_start[o + k] = run;
+        int c = st.b_cnt[o + k];
+        run += c;
+        n_nonempty += (c > 0);
+    }
+    st.next_left[slot] = -1;
+    st.next_right[slot] = -1;
+    st.split_pos[slot] = ptr + size;
+
+    if (st.cpl == 1 && size == 2) {  // creation.py:312-320
+        st.n_Lmax[node] = range_Lmax;
+        st.n_Rmin[node] = range_Rmin;
+        int c = atomicAdd(st.counters + 0, 2);
+        st.n_child[node] = c;
+        make_node(st, c, ptr, 1, !dim);
+        make_node(st, c + 1, ptr + 1, 1, !dim);
+        return;
+    }
+    if (n_nonempty <= 1) {  // one bucket holds everything, creation.py:345-358
+        if (!st.n_tried[node]) {
+            st.n_tried[node] = 1;
+            st.n_dim[node] = (uint8_t)(!dim);
+            int ns = atomicAdd(st.counters + 1, 1);
+            st.next_active[ns] = node;
+            st.next_left[slot] = ns;
+            st.next_right[slot] = ns;
+        }  // else: stays a (possibly oversized) leaf, Lmax = Rmin = -1 already, flipped dim kept
+        return;
+    }
+    // split_plane over the non-empty buckets, creation.py:174-213
+    double plane_min_cost = FLOAT_MAX;
+    int plane_k = -1;      // original index of the first bucket right of the plane
+    int left_count = 0;
+    {
+        int bbs_in_left = 0;
+        int prev = -1;
+        for (int k = 0; k < nb; k++) {
+            int c = st.b_cnt[o + k];
+            if (c == 0) continue;
+            if (prev >= 0) {
+                bbs_in_left += st.b_cnt[o + prev];
+                int bbs_in_right = size - bbs_in_left;
+                double cur_Lmax = dec(st.b_max[o + prev]);
+                double next_Rmin = dec(st.b_min[o + k]);
+                double left_volume = (cur_Lmax - range_Rmin) / bucket_length;
+                double right_volume = (range_Lmax - next_Rmin) / bucket_length;
+                double plane_cost = left_volume * (double)bbs_in_left + right_volume * (double)bbs_in_right;
+                if (plane_cost < plane_min_cost) {
+                    plane_min_cost = plane_cost;
+                    plane_k = k;
+                    left_count = bbs_in_left;
+                }
+            }
+            prev = k;
+        }
+    }
+    if (plane_k < 0) {  // every cost NaN / not below FLOAT_MAX: the reference indexes out of range
+        atomicExch(st.counters + 2, CT_ERR_VALUE);
+        return;
+    }
+    double Lmax = FLOAT_MIN, Rmin = FLOAT_MAX;
+    for (int k = 0; k < nb; k++) {
+        if (st.b_cnt[o + k] == 0) continue;
+        if (k < plane_k) {
+            double v = dec(st.b_max[o + k]);
+            if (v > Lmax) Lmax = v;
+        } else {
+            double v = dec(st.b_min[o + k]);
+            if (v < Rmin) Rmin = v;
+        }
+    }
+    st.n_Lmax[node] = Lmax;
+    st.n_Rmin[node] = Rmin;
+    int left_size = left_count, right_size = size - left_count;
+    int c = atomicAdd(st.counters + 0, 2);
+    st.n_child[node] = c;
+    make_node(st, c, ptr, left_size, !dim);
+    make_node(st, c + 1, ptr + left_size, right_size, !dim);
+    st.split_pos[slot] = ptr + left_size;
+    if (left_size > st.cpl) {
+        int ns = atomicAdd(st.counters + 1, 1);
+        st.next_active[ns] = c;
+        st.next_left[slot] = ns;
+    }
+    if (right_size > st.cpl) {
+        int ns = atomicAdd(st.counters + 1, 1);
+        st.next_active[ns] = c + 1;
+        st.next_right[slot] = ns;
+    }
+}
+
+// one-hot counters of 4 consecutive buckets, scanned over all positions
+struct OneHot4 {
+    const int32_t *seg;
+    const uint8_t *bkt;
+    int group;
+    __device__ uint4 operator()(int64_t pos) const {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (seg[pos] >= 0) {
+            int k = (int)bkt[pos] - 4 * group;
+            if (k == 0) r.x = 1;
+            else if (k == 1) r.y = 1;
+            else if (k == 2) r.z = 1;
+            else if (k == 3) r.w = 1;
+        }
+        return r;
+    }
+};
+struct Add4 {
+    __device__ uint4 operator()(const uint4 &a, const uint4 &b) const { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+};
+
+CT_DEV unsigned pick4(const uint4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// rank of an element among the same-bucket elements of its node that precede it (stable_partition keeps order)
+__global__ void __launch_bounds__(BB) k_rank(BuildState st, const uint4 *__restrict__ scan, int group, int64_t n, int32_t *__restrict__ rank) {
+    int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (pos >= n) return;
+    int slot = st.seg[pos];
+    if (slot < 0) return;
+    int k = (int)st.bkt[pos] - 4 * group;
+    if (k < 0 || k > 3) return;
+    int node = st.active[slot];
+    int ptr = st.n_ptr[node];
+    rank[pos] = (int32_t)(pick4(scan[pos], k) - pick4(scan[ptr], k));
+}
+
+__global__ void __launch_bounds__(BB) k_scatter(BuildState st, const int32_t *__restrict__ idx_in, const int32_t *__restrict__ rank,
+                                               int64_t n, int32_t *__restrict__ idx_out, int32_t *__restrict__ seg_out) {
+    int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (pos >= n) return;
+    int slot = st.seg[pos];
+    if (slot < 0) {
+        idx_out[pos] = idx_in[pos];
+        seg_out[pos] = -1;
+        return;
+    }
+    int node = st.active[slot];
+    int k = st.bkt[pos];
+    int np = st.n_ptr[node] + st.b_start[(int64_t)slot * st.nb + k] + rank[pos];
+    idx_out[np] = idx_in[pos];
+    seg_out[np] = (np < st.split_pos[slot]) ? st.next_left[slot] : st.next_right[slot];
+}
+
+__global__ void __launch_bounds__(BB) k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void __launch_bounds__(BB) k_iota(int32_t *p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+// ---- renumbering to the reference's node order --------------------------------------------------------------
+// splits[b] = number of splitting nodes in the subtree of b (children are always created in a later wave)
+__global__ void __launch_bounds__(BB) k_subtree_splits(const int32_t *__restrict__ n_child, int lo, int hi, int32_t *__restrict__ splits) {
+    int b = lo + blockIdx.x * BB + threadIdx.x;
+    if (b >= hi) return;
+    int c = n_child[b];
+    splits[b] = (c < 0) ? 0 : 1 + splits[c] + splits[c + 1];
+}
+// rank[b] = pre-order (left first) index of b among the splitting nodes; children of rank r get 1 + 2r, 2 + 2r
+__global__ void __launch_bounds__(BB) k_preorder(const int32_t *__restrict__ n_child, const int32_t *__restrict__ splits, int lo, int hi,
+                                                 int32_t *__restrict__ rank, int32_t *__restrict__ final_index,
+                                                 int32_t *__restrict__ level, int32_t *__restrict__ max_level) {
+    int b = lo + blockIdx.x * BB + threadIdx.x;
+    if (b >= hi) return;
+    int c = n_child[b];
+    if (c < 0) return;
+    int r = rank[b];
+    final_index[c] = 1 + 2 * r;
+    final_index[c + 1] = 2 + 2 * r;
+    rank[c] = r + 1;
+    rank[c + 1] = r + 1 + splits[c];
+    int l = level[b] + 1;
+    level[c] = l;
+    level[c + 1] = l;
+    atomicMax(max_level, l);
+}
+__global__ void __launch_bounds__(BB) k_emit_nodes(BuildState st, const int32_t *__restrict__ rank, const int32_t *__restrict__ final_index,
+                                                  int n_nodes, Node32 *__restrict__ out) {
+    int b = blockIdx.x * BB + threadIdx.x;
+    if (b >= n_nodes) return;
+    Node32 nd;
+    nd.Lmax = st.n_Lmax[b];
+    nd.Rmin = st.n_Rmin[b];
+    nd.child = st.n_child[b] < 0 ? -1 : 1 + 2 * rank[b];
+    nd.ptr = st.n_ptr[b];
+    nd.size = st.n_size[b];
+    nd.dim = st.n_dim[b];
+    out[final_index[b]] = nd;
+}
+
+static int64_t pessimistic_n_nodes(int64_t n_elements) {  // creation.py:216-230
+    int64_t n_nodes = n_elements;
+    int64_t nodes = (n_elements + 1) / 2;
+    while (nodes > 1) {
+        n_nodes += nodes;
+        nodes = (nodes + 1) / 2;
+    }
+    return n_nodes + 1;
+}
+
+static int build_tree(ct_tree *tree, cudaStream_t s) {
+    const int64_t n = tree->n_elem;
+    const int nb = tree->n_buckets, cpl = tree->cells_per_leaf;
+    const int64_t cap_nodes = pessimistic_n_nodes(n) + 2;
+    // an active node holds more than cells_per_leaf elements
+    const int64_t cap_active = n / (cpl + 1) + 2;
+
+    Scratch<int32_t> idx_a, idx_b, seg_a, seg_b, rank, n_ptr, n_size, n_child, act_a, act_b, b_cnt, b_start, next_left, next_right,
+        split_pos, counters, splits, pre_rank, final_index, level;
+    Scratch<uint8_t> bkt, n_dim, n_tried;
+    Scratch<double> n_Lmax, n_Rmin;
+    Scratch<unsigned long long> a_min, a_max, b_min, b_max;
+    Scratch<uint4> scan;
+    Scratch<char> scan_tmp;
+
+    CT_CHECK(idx_a.alloc(n, s));
+    CT_CHECK(idx_b.alloc(n, s));
+    CT_CHECK(seg_a.alloc(n, s));
+    CT_CHECK(seg_b.alloc(n, s));
+    CT_CHECK(rank.alloc(n, s));
+    CT_CHECK(bkt.alloc(n, s));
+    CT_CHECK(scan.alloc(n, s));
+    CT_CHECK(n_ptr.alloc(cap_nodes, s));
+    CT_CHECK(n_size.alloc(cap_nodes, s));
+    CT_CHECK(n_child.alloc(cap_nodes, s));
+    CT_CHECK(n_dim.alloc(cap_nodes, s));
+    CT_CHECK(n_tried.alloc(cap_nodes, s));
+    CT_CHECK(n_Lmax.alloc(cap_nodes, s));
+    CT_CHECK(n_Rmin.alloc(cap_nodes, s));
+    CT_CHECK(act_a.alloc(cap_active, s));
+    CT_CHECK(act_b.alloc(cap_active, s));
+    CT_CHECK(a_min.alloc(cap_active, s));
+    CT_CHECK(a_max.alloc(cap_active, s));
+    CT_CHECK(b_cnt.alloc(cap_active * nb, s));
+    CT_CHECK(b_min.alloc(cap_active * nb, s));
+    CT_CHECK(b_max.alloc(cap_active * nb, s));
+    CT_CHECK(b_start.alloc(cap_active * nb, s));
+    CT_CHECK(next_left.alloc(cap_active, s));
+    CT_CHECK(next_right.alloc(cap_active, s));
+    CT_CHECK(split_pos.alloc(cap_active, s));
+    CT_CHECK(counters.alloc(4, s));
+
+    size_t scan_bytes = 0;
+    {
+        OneHot4 oh{seg_a.p, bkt.p, 0};
+        auto in = cub::TransformInputIterator<uint4, OneHot4, cub::CountingInputIterator<int64_t>>(cub::CountingInputIterator<int64_t>(0), oh);
+        CT_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, in, scan.p, Add4(), make_uint4(0, 0, 0, 0), n, s));
+    }
+    CT_CHECK(scan_tmp.alloc(scan_bytes, s));
+
+    // root: Node(-1, -1.0, -1.0, ptr=0, size=n, dim=False), creation.py:399-401
+    k_iota<<<grid_for(n, BB), BB, 0, s>>>(idx_a.p, n);
+    CT_LAUNCH_CHECK();
+    k_fill_i32<<<grid_for(n, BB), BB, 0, s>>>(seg_a.p, n, n > cpl ? 0 : -1);
+    CT_LAUNCH_CHECK();
+    {
+        int32_t h_ptr = 0, h_size = (int32_t)n, h_child = -1, h_act = 0;
+        uint8_t h_zero = 0;
+        double h_m1 = -1.0;
+        int32_t h_counters[4] = {1, 0, 0, 0};
+        CT_CUDA(cudaMemcpyAsync(n_ptr.p, &h_ptr, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_size.p, &h_size, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_child.p, &h_child, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_dim.p, &h_zero, 1, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_tried.p, &h_zero, 1, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_Lmax.p, &h_m1, 8, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(n_Rmin.p, &h_m1, 8, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(act_a.p, &h_act, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(counters.p, h_counters, 16, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaStreamSynchronize(s));  // the host temporaries above go out of scope
+    }
+
+    BuildState st;
+    st.bb = tree->bb_coords;
+    st.bkt = bkt.p;
+    st.n_ptr = n_ptr.p; st.n_size = n_size.p; st.n_child = n_child.p;
+    st.n_dim = n_dim.p; st.n_tried = n_tried.p; st.n_Lmax = n_Lmax.p; st.n_Rmin = n_Rmin.p;
+    st.a_min = a_min.p; st.a_max = a_max.p;
+    st.b_cnt = b_cnt.p; st.b_min = b_min.p; st.b_max = b_max.p; st.b_start = b_start.p;
+    st.next_left = next_left.p; st.next_right = next_right.p; st.split_pos = split_pos.p;
+    st.counters = counters.p;
+    st.nb = nb; st.cpl = cpl;
+
+    int32_t *idx_cur = idx_a.p, *idx_nxt = idx_b.p, *seg_cur = seg_a.p, *seg_nxt = seg_b.p, *act_cur = act_a.p, *act_nxt = act_b.p;
+    std::vector<int32_t> wave_start;  // node-count at the start of every wave
+    wave_start.push_back(0);
+    int n_active = n > cpl ? 1 : 0;
+    int32_t node_count = 1;
+    const int n_groups = (nb + 3) / 4;
+    while (n_active > 0) {
+        wave_start.push_back(node_count);
+        st.seg = seg_cur;
+        st.active = act_cur;
+        st.next_active = act_nxt;
+        k_init_slots<<<grid_for(n_active, BB), BB, 0, s>>>(st, n_active);
+        CT_LAUNCH_CHECK();
+        k_range<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, n);
+        CT_LAUNCH_CHECK();
+        k_bucket<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, n);
+        CT_LAUNCH_CHECK();
+        k_decide<<<grid_for(n_active, 128), 128, 0, s>>>(st, n_active);
+        CT_LAUNCH_CHECK();
+        for (int g = 0; g < n_groups; g++) {
+            OneHot4 oh{seg_cur, bkt.p, g};
+            auto in = cub::TransformInputIterator<uint4, OneHot4, cub::CountingInputIterator<int64_t>>(cub::CountingInputIterator<int64_t>(0), oh);
+            size_t bytes = scan_bytes;
+            CT_CUDA(cub::DeviceScan::ExclusiveScan(scan_tmp.p, bytes, in, scan.p, Add4(), make_uint4(0, 0, 0, 0), n, s));
+            count_launch(2);
+            k_rank<<<grid_for(n, BB), BB, 0, s>>>(st, scan.p, g, n, rank.p);
+            CT_LAUNCH_CHECK();
+        }
+        k_scatter<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, rank.p, n, idx_nxt, seg_nxt);
+        CT_LAUNCH_CHECK();
+        int32_t h[4];
+        CT_CUDA(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+        if (h[2] == CT_ERR_UNBUCKETABLE) {
+            set_error("tree construction: the centroid of an element falls in no bucket (list index out of range)");
+            return CT_ERR_UNBUCKETABLE;
+        }
+        if (h[2] != 0) {
+            set_error("tree construction: no split plane has a finite cost (list index out of range)");
+            return CT_ERR_UNBUCKETABLE;
+        }
+        node_count = h[0];
+        n_active = h[1];
+        int32_t zero = 0;
+        CT_CUDA(cudaMemcpyAsync(counters.p + 1, &zero, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+        std::swap(idx_cur, idx_nxt);
+        std::swap(seg_cur, seg_nxt);
+        std::swap(act_cur, act_nxt);
+        if ((int64_t)wave_start.size() > 4 * (int64_t)n + 64) {
+            set_error("tree construction did not terminate");
+            return CT_ERR_VALUE;
+        }
+    }
+    wave_start.push_back(node_count);
+
+    // renumber: creation order -> the reference's depth-first numbering
+    CT_CHECK(splits.alloc(node_count, s));
+    CT_CHECK(pre_rank.alloc(node_count, s));
+    CT_CHECK(final_index.alloc(node_count, s));
+    CT_CHECK(level.alloc(node_count, s));
+    Scratch<int32_t> max_level;
+    CT_CHECK(max_level.alloc(1, s));
+    {
+        int32_t zero = 0, one = 1;
+        CT_CUDA(cudaMemcpyAsync(pre_rank.p, &zero, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(final_index.p, &zero, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(level.p, &one, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaMemcpyAsync(max_level.p, &one, 4, cudaMemcpyHostToDevice, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    const int n_waves = (int)wave_start.size() - 1;
+    for (int w = n_waves - 1; w >= 0; w--) {
+        int lo = wave_start[w], hi = wave_start[w + 1];
+        if (hi <= lo) continue;
+        k_subtree_splits<<<grid_for(hi - lo, BB), BB, 0, s>>>(n_child.p, lo, hi, splits.p);
+        CT_LAUNCH_CHECK();
+    }
+    for (int w = 0; w < n_waves; w++) {
+        int lo = wave_start[w], hi = wave_start[w + 1];
+        if (hi <= lo) continue;
+        k_preorder<<<grid_for(hi - lo, BB), BB, 0, s>>>(n_child.p, splits.p, lo, hi, pre_rank.p, final_index.p, level.p, max_level.p);
+        CT_LAUNCH_CHECK();
+    }
+    CT_CUDA(cudaMalloc((void **)&tree->nodes, sizeof(Node32) * (size_t)node_count));
+    k_emit_nodes<<<grid_for(node_count, BB), BB, 0, s>>>(st, pre_rank.p, final_index.p, node_count, tree->nodes);
+    CT_LAUNCH_CHECK();
+    CT_CUDA(cudaMalloc((void **)&tree->bb_indices, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+    CT_CUDA(cudaMemcpyAsync(tree->bb_indices, idx_cur, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    int32_t h_level = 1;
+    CT_CUDA(cudaMemcpyAsync(&h_level, max_level.p, 4, cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    tree->n_nodes = node_count;
+    tree->depth = h_level;
+    return CT_OK;
+}
+
+static int ensure_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 64 && done[device]) return CT_OK;
+    cudaMemPool_t pool;
+    CT_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;  // keep freed scratch memory cached in the pool
+    CT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    if (device < 64) done[device] = true;
+    return CT_OK;
+}
+
+// bbox_tree + default tolerance from the device bb_coords
+static int finish_bounds(ct_tree *tree, cudaStream_t s) {
+    Scratch<unsigned long long> red;
+    CT_CHECK(red.alloc(5, s));
+    unsigned long long init[5] = {enc_host(FLOAT_MAX), enc_host(FLOAT_MIN), enc_host(FLOAT_MAX), enc_host(FLOAT_MIN), enc_host(FLOAT_MIN)};
+    CT_CUDA(cudaMemcpyAsync(red.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    int grid = grid_for(tree->n_elem, BB);
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_bbox_reduce<<<grid, BB, 0, s>>>(tree->bb_coords, tree->n_elem, red.p);
+    CT_LAUNCH_CHECK();
+    unsigned long long h[5];
+    CT_CUDA(cudaMemcpyAsync(h, red.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 4; k++) tree->bbox[k] = dec_host(h[k]);
+    double diag = dec_host(h[4]);
+    double tol = TOLERANCE_FACTOR * diag;  // default_tolerance, celltree_base.py:51-52
+    tree->default_tolerance = tol > MIN_TOLERANCE ? tol : MIN_TOLERANCE;
+    return CT_OK;
+}
+
+static int upload_mesh(ct_tree *tree, const double *vertices, const int64_t *elements, int32_t mem, cudaStream_t s) {
+    const int64_t nv = tree->n_vertex, ne = tree->n_elem;
+    const int M = tree->M;
+    CT_CUDA(cudaMalloc((void **)&tree->vertices, sizeof(double2) * (size_t)(nv > 0 ? nv : 1)));
+    CT_CUDA(cudaMalloc((void **)&tree->elements, sizeof(int32_t) * (size_t)(ne * M > 0 ? ne * M : 1)));
+    CT_CUDA(cudaMalloc((void **)&tree->bb_coords, sizeof(double) * 4 * (size_t)(ne > 0 ? ne : 1)));
+    cudaMemcpyKind kind = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CT_CUDA(cudaMemcpyAsync(tree->vertices, vertices, sizeof(double2) * (size_t)nv, kind, s));
+    if (mem == CT_MEM_DEVICE) {
+        CT_CHECK(launch_narrow(elements, ne * M, tree->elements, s));
+    } else {
+        Scratch<int64_t> tmp;
+        CT_CHECK(tmp.alloc((size_t)ne * M, s));
+        CT_CUDA(cudaMemcpyAsync(tmp.p, elements, sizeof(int64_t) * (size_t)ne * M, cudaMemcpyHostToDevice, s));
+        CT_CHECK(launch_narrow(tmp.p, ne * M, tree->elements, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    return CT_OK;
+}
+
+static int check_mesh_args(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem, int32_t n_max_vert,
+                           int32_t kind) {
+    if (!vertices || !elements || n_vertex <= 0 || n_elem <= 0) {
+        set_error("zero-size array to reduction operation minimum which has no identity (empty mesh)");
+        return CT_ERR_VALUE;
+    }
+    if (kind == CT_KIND_FACES && (n_max_vert < 3 || n_max_vert > MAX_N_VERTEX)) {
+        set_error("faces must have between 3 and 32 columns");
+        return CT_ERR_VALUE;
+    }
+    if (kind == CT_KIND_EDGES && n_max_vert != 2) {
+        set_error("edges must have shape (n_edge, 2)");
+        return CT_ERR_VALUE;
+    }
+    if (kind != CT_KIND_FACES && kind != CT_KIND_EDGES) {
+        set_error("unknown tree kind");
+        return CT_ERR_VALUE;
+    }
+    if (n_vertex >= (1LL << 31) || n_elem >= (1LL << 31) - 2) {
+        set_error("mesh too large for 32-bit device indices");
+        return CT_ERR_VALUE;
+    }
+    return CT_OK;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_tree_create(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem, int32_t n_max_vert,
+                              int32_t kind, int32_t n_buckets, int32_t cells_per_leaf, double edge_tolerance, int32_t mem,
+                              ct_tree **out) {
+    if (!out) {
+        set_error("ct_tree_create: null output");
+        return CT_ERR_VALUE;
+    }
+    if (n_buckets < 2) {
+        set_error("n_buckets must be >= 2");
+        return CT_ERR_VALUE;
+    }
+    if (n_buckets > 255) {
+        set_error("n_buckets must be <= 255 in the B200 build");
+        return CT_ERR_VALUE;
+    }
+    if (cells_per_leaf < 1) {
+        set_error("cells_per_leaf must be >= 1");
+        return CT_ERR_VALUE;
+    }
+    CT_CHECK(check_mesh_args(vertices, n_vertex, elements, n_elem, n_max_vert, kind));
+    int device = 0;
+    CT_CUDA(cudaGetDevice(&device));
+    CT_CHECK(ensure_pool(device));
+    cudaStream_t s = current_stream();
+    ct_tree *tree = new ct_tree();
+    tree->device = device;
+    tree->n_vertex = n_vertex;
+    tree->n_elem = n_elem;
+    tree->M = n_max_vert;
+    tree->kind = kind;
+    tree->n_buckets = n_buckets;
+    tree->cells_per_leaf = cells_per_leaf;
+    auto body = [&]() -> int {
+        CT_CHECK(upload_mesh(tree, vertices, elements, mem, s));
+        cudaEvent_t e0, e1;
+        CT_CUDA(cudaEventCreate(&e0));
+        CT_CUDA(cudaEventCreate(&e1));
+        CT_CUDA(cudaEventRecord(e0, s));
+        if (kind == CT_KIND_FACES) {
+            CT_CHECK(launch_counter_clockwise(tree->vertices, tree->elements, n_elem, n_max_vert, s));
+            CT_CHECK(launch_face_bboxes(tree->vertices, tree->elements, n_elem, n_max_vert, tree->bb_coords, s));
+        } else {
+            k_edge_bboxes<<<grid_for(n_elem, BB), BB, 0, s>>>(tree->vertices, tree->elements, n_elem, edge_tolerance, tree->bb_coords);
+            CT_LAUNCH_CHECK();
+        }
+        CT_CHECK(finish_bounds(tree, s));
+        CT_CHECK(build_tree(tree, s));
+        CT_CUDA(cudaEventRecord(e1, s));
+        CT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        tree->build_ms = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return CT_OK;
+    };
+    int status = body();
+    if (status != CT_OK) {
+        ct_tree_destroy(tree);
+        return status;
+    }
+    *out = tree;
+    return CT_OK;
+}
+
+extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem,
+                                   int32_t n_max_vert, int32_t kind, const ct_node41 *nodes, int64_t n_nodes,
+                                   const int64_t *bb_indices, const double *bb_coords, int32_t cells_per_leaf, int32_t mem,
+                                   ct_tree **out) {
+    if (!out || !nodes || !bb_indices || !bb_coords || n_nodes <= 0) {
+        set_error("ct_tree_from_arrays: null argument");
+        return CT_ERR_VALUE;
+    }
+    CT_CHECK(check_mesh_args(vertices, n_vertex, elements, n_elem, n_max_vert, kind));
+    int device = 0;
+    CT_CUDA(cudaGetDevice(&device));
+    CT_CHECK(ensure_pool(device));
+    cudaStream_t s = current_stream();
+    ct_tree *tree = new ct_tree();
+    tree->device = device;
+    tree->n_vertex = n_vertex;
+    tree->n_elem = n_elem;
+    tree->M = n_max_vert;
+    tree->kind = kind;
+    tree->n_buckets = 0;
+    tree->cells_per_leaf = cells_per_leaf;
+    tree->n_nodes = n_nodes;
+    auto body = [&]() -> int {
+        CT_CHECK(upload_mesh(tree, vertices, elements, mem, s));
+        cudaMemcpyKind kind_cp = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CT_CUDA(cudaMemcpyAsync(tree->bb_coords, bb_coords, sizeof(double) * 4 * (size_t)n_elem, kind_cp, s));
+        CT_CUDA(cudaMalloc((void **)&tree->bb_indices, sizeof(int32_t) * (size_t)n_elem));
+        CT_CUDA(cudaMalloc((void **)&tree->nodes, sizeof(Node32) * (size_t)n_nodes));
+        {
+            Scratch<int64_t> tmp;
+            const int64_t *src = bb_indices;
+            if (mem != CT_MEM_DEVICE) {
+                CT_CHECK(tmp.alloc(n_elem, s));
+                CT_CUDA(cudaMemcpyAsync(tmp.p, bb_indices, sizeof(int64_t) * (size_t)n_elem, cudaMemcpyHostToDevice, s));
+                src = tmp.p;
+            }
+            CT_CHECK(launch_narrow(src, n_elem, tree->bb_indices, s));
+            Scratch<unsigned char> packed;
+            size_t bytes = (size_t)n_nodes * NODE41;
+            CT_CHECK(packed.alloc(bytes + 4, s));
+            CT_CUDA(cudaMemcpyAsync(packed.p, nodes, bytes, kind_cp, s));
+            k_unpack_nodes<<<grid_for(n_nodes, BB), BB, 0, s>>>(packed.p, n_nodes, tree->nodes);
+            CT_LAUNCH_CHECK();
+            Scratch<int32_t> parent, max_depth;
+            CT_CHECK(parent.alloc(n_nodes, s));
+            CT_CHECK(max_depth.alloc(1, s));
+            k_fill_i32<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, -1);
+            CT_LAUNCH_CHECK();
+            CT_CUDA(cudaMemsetAsync(max_depth.p, 0, 4, s));
+            k_parents<<<grid_for(n_nodes, BB), BB, 0, s>>>(tree->nodes, n_nodes, parent.p);
+            CT_LAUNCH_CHECK();
+            k_depth<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, max_depth.p);
+            CT_LAUNCH_CHECK();
+            int32_t d = 0;
+            CT_CUDA(cudaMemcpyAsync(&d, max_depth.p, 4, cudaMemcpyDeviceToHost, s));
+            CT_CUDA(cudaStreamSynchronize(s));
+            tree->depth = d;
+        }
+        CT_CHECK(finish_bounds(tree, s));
+        return CT_OK;
+    };
+    int status = body();
+    if (status != CT_OK) {
+        ct_tree_destroy(tree);
+        return status;
+    }
+    *out = tree;
+    return CT_OK;
+}
+
+extern "C" int ct_tree_get_info(const ct_tree *tree, ct_tree_info *info) {
+    if (!tree || !info) {
+        set_error("ct_tree_get_info: null argument");
+        return CT_ERR_VALUE;
+    }
+    info->n_vertex = tree->n_vertex;
+    info->n_elem = tree->n_elem;
+    info->n_nodes = tree->n_nodes;
+    info->n_max_vert = tree->M;
+    info->kind = tree->kind;
+    info->n_buckets = tree->n_buckets;
+    info->cells_per_leaf = tree->cells_per_leaf;
+    info->depth = tree->depth;
+    info->reserved = 0;
+    for (int k = 0; k < 4; k++) info->bbox[k] = tree->bbox[k];
+    info->default_tolerance = tree->default_tolerance;
+    info->build_ms = tree->build_ms;
+    return CT_OK;
+}
+
+extern "C" int ct_tree_download(const ct_tree *tree, ct_node41 *nodes, int64_t *bb_indices, double *bb_coords, int64_t *elements,
+                                double *bb_distances, int32_t mem) {
+    if (!tree) {
+        set_error("ct_tree_download: null tree");
+        return CT_ERR_VALUE;
+    }
+    CT_CUDA(cudaSetDevice(tree->device));
+    cudaStream_t s = current_stream();
+    cudaMemcpyKind kind = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const int64_t n = tree->n_elem;
+    if (nodes) {
+        Scratch<unsigned char> packed;
+        size_t bytes = (size_t)tree->n_nodes * NODE41;
+        CT_CHECK(packed.alloc(bytes + 4, s));
+        k_pack_nodes<<<grid_for(tree->n_nodes, BB), BB, 0, s>>>(tree->nodes, tree->n_nodes, packed.p);
+        CT_LAUNCH_CHECK();
+        CT_CUDA(cudaMemcpyAsync(nodes, packed.p, bytes, kind, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    if (bb_indices) {
+        Scratch<int64_t> wide;
+        int64_t *dst = bb_indices;
+        if (mem != CT_MEM_DEVICE) {
+            CT_CHECK(wide.alloc(n, s));
+            dst = wide.p;
+        }
+        CT_CHECK(launch_widen(tree->bb_indices, n, dst, s));
+        if (mem != CT_MEM_DEVICE) CT_CUDA(cudaMemcpyAsync(bb_indices, dst, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    if (bb_coords) CT_CUDA(cudaMemcpyAsync(bb_coords, tree->bb_coords, sizeof(double) * 4 * (size_t)n, kind, s));
+    if (elements) {
+        Scratch<int64_t> wide;
+        int64_t *dst = elements;
+        int64_t count = n * tree->M;
+        if (mem != CT_MEM_DEVICE) {
+            CT_CHECK(wide.alloc(count, s));
+            dst = wide.p;
+        }
+        CT_CHECK(launch_widen(tree->elements, count, dst, s));
+        if (mem != CT_MEM_DEVICE) CT_CUDA(cudaMemcpyAsync(elements, dst, sizeof(int64_t) * (size_t)count, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    if (bb_distances) {
+        Scratch<double> dist;
+        double *dst = bb_distances;
+        if (mem != CT_MEM_DEVICE) {
+            CT_CHECK(dist.alloc(3 * (size_t)n, s));
+            dst = dist.p;
+        }
+        k_bb_distances<<<grid_for(n, BB), BB, 0, s>>>(tree->bb_coords, n, dst);
+        CT_LAUNCH_CHECK();
+        if (mem != CT_MEM_DEVICE) CT_CUDA(cudaMemcpyAsync(bb_distances, dst, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+    }
+    CT_CUDA(cudaStreamSynchronize(s));
+    return CT_OK;
+}
+
+extern "C" void ct_tree_destroy(ct_tree *tree) {
+    if (!tree) return;
+    cudaFree(tree->nodes);
+    cudaFree(tree->bb_indices);
+    cudaFree(tree->bb_coords);
+    cudaFree(tree->elements);
+    cudaFree(tree->vertices);
+    delete tree;
+}

@@ -1,0 +1,152 @@
+// common.cuh -- device tree layout, error plumbing and small helpers shared by build.cu / query.cu.
+//
+// Everything in csrc/ is compiled with -fmad=false: the reference (Numba/LLVM) emits no fused
+// multiply-adds, and bucket membership / on-edge decisions / pair lists depend on the last bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/celltree_b200.h"
+
+namespace ct {
+
+// ---- device node: 32 bytes, one L2 sector ---------------------------------------------------------
+// Reference NodeDType is 41 bytes unaligned (constants.py:91-106); the device copy is repacked so that
+// a node is exactly one 32-byte sector and is fetched with two 16-byte loads.
+struct __align__(16) Node32 {
+    double Lmax;
+    double Rmin;
+    int32_t child;  // left child; right = child + 1; -1 for a leaf
+    int32_t ptr;    // into bb_indices
+    int32_t size;
+    int32_t dim;    // 0 = x, 1 = y
+};
+static_assert(sizeof(Node32) == 32, "Node32 must be one 32-byte sector");
+
+struct TreeView {  // passed by value to kernels
+    const Node32 *nodes;
+    const int32_t *bb_indices;
+    const double *bb_coords;  // (n_elem, 4): xmin, xmax, ymin, ymax
+    const int32_t *elements;  // (n_elem, M) vertex ids, -1 filled
+    const double2 *vertices;
+    int32_t M;
+    int32_t n_elem;
+    double bbox[4];
+};
+
+constexpr int MAX_N_VERTEX = 32;      // constants.py:128
+constexpr double MIN_TOLERANCE = 1e-15;   // constants.py:140
+constexpr double TOLERANCE_FACTOR = 1e-12;  // constants.py:141
+constexpr double FLOAT_MAX = 1.7976931348623157e308;   // constants.py:144
+constexpr double FLOAT_MIN = -1.7976931348623157e308;  // constants.py:143
+
+// ---- error plumbing ----------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+cudaStream_t current_stream();
+void count_launch(int n = 1);
+
+#define CT_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            char _buf[512];                                                                            \
+            snprintf(_buf, sizeof(_buf), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                     __LINE__, cudaGetErrorString(_e));                                                \
+            ct::set_error(_buf);                                                                       \
+            return CT_ERR_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+#define CT_CHECK(expr)            \
+    do {                          \
+        int _s = (expr);          \
+        if (_s != CT_OK) return _s; \
+    } while (0)
+
+#define CT_LAUNCH_CHECK()                 \
+    do {                                  \
+        ct::count_launch();               \
+        CT_CUDA(cudaGetLastError());      \
+    } while (0)
+
+// Stream-ordered scratch allocation (cudaMallocAsync pool: no device-wide sync, memory is cached).
+template <typename T>
+inline int dalloc(T **p, size_t count, cudaStream_t s) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CT_CUDA(cudaMallocAsync((void **)p, count * sizeof(T), s));
+    return CT_OK;
+}
+inline void dfree(void *p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
+// Owns a stream-ordered allocation for the duration of a call.
+template <typename T>
+struct Scratch {
+    T *p = nullptr;
+    cudaStream_t s = 0;
+    Scratch() = default;
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    ~Scratch() { dfree(p, s); }
+    int alloc(size_t count, cudaStream_t stream) {
+        dfree(p, s);
+        s = stream;
+        return dalloc(&p, count, stream);
+    }
+    T *release() {
+        T *r = p;
+        p = nullptr;
+        return r;
+    }
+    operator T *() const { return p; }
+};
+
+inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- the device tree ---------------------------------------------------------------------------------
+}  // namespace ct
+
+struct ct_tree {
+    int64_t n_vertex = 0, n_elem = 0, n_nodes = 0;
+    int32_t M = 0, kind = 0, n_buckets = 0, cells_per_leaf = 0, depth = 0;
+    double bbox[4] = {0, 0, 0, 0};
+    double default_tolerance = 0.0;
+    double build_ms = 0.0;
+    int device = 0;
+    // device arrays (owned)
+    ct::Node32 *nodes = nullptr;
+    int32_t *bb_indices = nullptr;
+    double *bb_coords = nullptr;
+    int32_t *elements = nullptr;
+    double2 *vertices = nullptr;
+
+    ct::TreeView view() const {
+        ct::TreeView v;
+        v.nodes = nodes;
+        v.bb_indices = bb_indices;
+        v.bb_coords = bb_coords;
+        v.elements = elements;
+        v.vertices = vertices;
+        v.M = M;
+        v.n_elem = (int32_t)n_elem;
+        for (int k = 0; k < 4; k++) v.bbox[k] = bbox[k];
+        return v;
+    }
+};
+
+struct ct_result {
+    int64_t size = 0;
+    int32_t width = 0;   // payload doubles per pair
+    int32_t *i = nullptr;  // query index
+    int32_t *j = nullptr;  // tree element index
+    double *payload = nullptr;
+};
