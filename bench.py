@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""
+bench.py -- BASELINE.json's headline metric on its headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric: locate_points queries/s.  Workload (config C2 of BASELINE.json / SURVEY.md 8d): 4096 x 4096
+structured quad mesh as CellTree2d (16 777 216 cells), 100 000 000 seeded random points per GPU.
+One "step" = one locate_points pass over the whole batch.
+
+  value      device-resident throughput: points and results live in HBM, CUDA events around K steps.
+  e2e        the same call through the public API with HOST (pinned) buffers: host->device copy of the
+             points and device->host copy of the indices inside the timed region.
+  roofline   dominant kernel (k_locate_points): algorithmic bytes (918 B/query at C2) x queries
+             / its launch duration (CUDA events on the launching stream), against the measured HBM copy peak.
+  cpu_baseline  the CPU oracle (C restatement of the reference's algorithm, OpenMP over queries like the
+             reference's prange) timed on this box's host cores on a bounded prefix of the same points.
+
+Multi-GPU (torchrun, one rank per GPU): the tree is built on rank 0 and replicated by NCCL broadcast over
+NVLink; queries shard by rank with no data-path collective (weak scaling: every rank owns a full batch).
+
+--impl reference times the CPU oracle alone (all host threads) on the same configuration, each step a
+bounded prefix of the batch.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "locate_points queries/s"
+UNIT = "queries/s"
+# 16 B point + 8 B result + 24 node visits x 32 B + 1.5 cells x (4 B index + 16 B face row + 64 B vertices)
+ALGORITHMIC_BYTES_PER_QUERY = 918.0
+HBM_FALLBACK_GBS = 6650.0
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def workload():
+    nx = env_int("CELLTREE_BENCH_NX", 4096)
+    n_points = env_int("CELLTREE_BENCH_POINTS", 100_000_000)
+    name = f"C2: {nx}x{nx} structured quad mesh as CellTree2d ({nx * nx} cells), {n_points} random points locate_points"
+    return nx, n_points, name
+
+
+def measured_peak():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def cpu_oracle_rate(tree_data, tolerance, points, target_seconds=12.0):
+    """Time the CPU oracle's locate_points on a bounded prefix of `points`; returns (q/s, n, seconds, result)."""
+    import oracle
+
+    probe = min(len(points), 500_000)
+    t0 = time.perf_counter()
+    oracle.locate_points(points[:probe], tree_data, tolerance)
+    dt = time.perf_counter() - t0
+    rate = probe / max(dt, 1e-9)
+    n = int(min(len(points), max(probe, rate * target_seconds)))
+    t0 = time.perf_counter()
+    result = oracle.locate_points(points[:n], tree_data, tolerance)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, result
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's algorithm, all host threads, same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from numba_celltree_b200.synthetic import c2_points, quad_mesh
+
+    nx, n_points, name = workload()
+    sample = min(n_points, env_int("CELLTREE_BENCH_REFERENCE_SAMPLE", 4_000_000))
+    vertices, faces = quad_mesh(nx, nx)
+    t0 = time.perf_counter()
+    tree = oracle.CellTree2d(vertices, faces, -1)
+    build_s = time.perf_counter() - t0
+    points = c2_points(sample)
+    cores = oracle.num_threads()
+    for _ in range(args.warmup):
+        oracle.locate_points(points, tree.celltree_data, tree._tolerance)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.locate_points(points, tree.celltree_data, tree._tolerance)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": name, "step": f"first {sample} of the seed-42 points per step", "oracle_build_s": round(build_s, 2)},
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"first {sample} of the {n_points} seed-42 points, {args.steps} steps",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    from numba_celltree_b200 import CellTree2d, _lib
+    from numba_celltree_b200 import distributed as ctd
+    from numba_celltree_b200.synthetic import quad_mesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    _lib.check(lib.ct_set_device(local_rank))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+
+    nx, n_points, name = workload()
+    args.warmup = max(args.warmup, 3)
+
+    # ---- the tree: built on rank 0 on the device, replicated over NVLink -----------------------------------
+    t0 = time.perf_counter()
+    if rank == 0:
+        vertices, faces = quad_mesh(nx, nx)
+        tree = CellTree2d(vertices, faces, -1)
+        build_ms = tree.build_ms
+        del faces
+    else:
+        tree = None
+        build_ms = None
+    if world > 1:
+        tree = ctd.broadcast_tree(tree, src=0, device=device)
+    setup_s = time.perf_counter() - t0
+    tolerance = tree._default_tolerance()
+
+    # ---- this rank's batch of queries (seed 42 + rank), pinned on the host, resident on the device ----------
+    rng = np.random.default_rng(42 + rank)
+    host_points = torch.empty((n_points, 2), dtype=torch.float64).pin_memory()
+    host_np = host_points.numpy()
+    rng.random(out=host_np.reshape(-1))  # == default_rng(seed).uniform(0, 1, (n, 2))
+    host_out = torch.empty(n_points, dtype=torch.int64).pin_memory()
+    dev_points = host_points.to(device, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        import torch.distributed as dist
+
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps ---------------------------------------------------------------------------------
+    dev_out = None
+    for _ in range(args.warmup):
+        dev_out = tree.locate_points(dev_points)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.ct_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        dev_out = tree.locate_points(dev_points)
+    stop.record()
+    barrier()
+    launches = lib.ct_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(start.elapsed_time(stop))
+    ms_per_step = ms_total / args.steps
+    value = world * n_points / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel: one launch per step; time single launches with events on the launching stream ---------
+    kernel_ms = []
+    for _ in range(min(args.steps, 5)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tree.locate_points(dev_points)
+        e1.record()
+        torch.cuda.synchronize()
+        kernel_ms.append(e0.elapsed_time(e1))
+    kernel_avg_ms = float(np.mean(kernel_ms))
+    peak, peak_source = measured_peak()
+    achieved = ALGORITHMIC_BYTES_PER_QUERY * n_points / (kernel_avg_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": "k_locate_points<4,false>",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_source,
+        "algorithmic_bytes_per_query": ALGORITHMIC_BYTES_PER_QUERY,
+        "kernel_ms": kernel_avg_ms,
+    }
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():
+        try:
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get("k_locate_points_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with pinned host buffers --------------------------------------------------
+    out_np = host_out.numpy()
+    for _ in range(2):
+        tree.locate_points(host_np, out=out_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tree.locate_points(host_np, out=out_np)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {
+        "value": world * n_points * args.steps / e2e_s,
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(n_points * 16),
+        "d2h_bytes_per_step": int(n_points * 8),
+        "ms_per_step": 1e3 * e2e_s / args.steps,
+    }
+    same = bool(torch.equal(dev_out.cpu(), host_out))
+
+    # ---- CPU baseline + parity spot check (rank 0, single-GPU run only) ------------------------------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        data = tree.celltree_data  # mirrors of the device tree (bit-identical to the reference's arrays)
+        rate, n_cpu, secs, cpu_result = cpu_oracle_rate(data, tolerance, host_np)
+        cpu_baseline = {
+            "value": rate,
+            "unit": UNIT,
+            "cores": oracle.num_threads(),
+            "kind": "port",
+            "sample": f"first {n_cpu} of the {n_points} points, {secs:.1f} s, OpenMP static over queries",
+        }
+        parity = {"checked_queries": n_cpu, "bit_exact": bool(np.array_equal(cpu_result, out_np[:n_cpu]))}
+
+    # ---- second headline metric: intersect_faces pairs/s (C5), single GPU -----------------------------------------------
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = intersect_faces_metric(torch)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": name,
+                "per_gpu_queries": n_points,
+                "sharding": "tree replicated (NCCL broadcast), queries sharded by rank, no data-path collective",
+                "l2": "inputs larger than L2 (1.6 GB of points + 1.1 GB of tree per step vs 126 MB)",
+                "tree_build_ms": build_ms,
+                "setup_s": round(setup_s, 2),
+                "tree_depth": tree.depth,
+                "tolerance": tolerance,
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "parity": parity,
+            "e2e_equals_device_result": same,
+            "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def intersect_faces_metric(torch):
+    """C5: 1000 x 1000 quads intersect_faces against the 2M-triangle Delaunay tree (pairs/s, end to end)."""
+    from numba_celltree_b200 import CellTree2d
+    from numba_celltree_b200.synthetic import delaunay_mesh, quad_mesh
+
+    n_pts = env_int("CELLTREE_BENCH_C3_POINTS", 1_000_000)
+    nq = env_int("CELLTREE_BENCH_C5_NX", 1000)
+    try:
+        vertices, faces = delaunay_mesh(n_pts, seed=1234)
+    except Exception as e:  # scipy missing
+        return {"unavailable": str(e)}
+    tree = CellTree2d(vertices, faces, -1)
+    qv, qf = quad_mesh(nq, nq)
+    tree.intersect_faces(qv, qf, -1)
+    torch.cuda.synchronize()
+    times = []
+    n_pairs = 0
+    area = 0.0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        i, j, a = tree.intersect_faces(qv, qf, -1)
+        times.append(time.perf_counter() - t0)
+        n_pairs = len(i)
+        area = float(a.sum())
+    best = min(times)
+    return {
+        "metric": "intersect_faces pairs/s",
+        "value": n_pairs / best,
+        "unit": "pairs/s",
+        "pairs": n_pairs,
+        "seconds": best,
+        "sum_area": area,
+        "workload": f"C5: {nq}x{nq} quads intersect_faces against Delaunay({n_pts} pts) = {len(faces)} triangles; NumPy in, NumPy out",
+        "tree_build_ms": tree.build_ms,
+        "tree_depth": tree.depth,
+    }
+
+
+if __name__ == "__main__":
+    main()

@@ -90,12 +90,13 @@ class CellTree2d(CellTree2dBase):
     def _elements(self):
         return self.faces
 
-    def locate_points(self, points: FloatArray, tolerance: Optional[float] = None) -> IntArray:
+    def locate_points(self, points: FloatArray, tolerance: Optional[float] = None, *, out=None) -> IntArray:
         """
         Find the index of a face that contains a point (-1 if none); points within ``tolerance`` of an edge
         count as inside.  ``tolerance=None``: 1e-12 x the largest bounding-box diagonal (at least 1e-15).
+        ``out`` (extension): a preallocated intp result array, e.g. in pinned host memory.
         """
-        return self._locate_points(points, tolerance, with_weights=False)
+        return self._locate_points(points, tolerance, with_weights=False, out=out)
 
     def compute_barycentric_weights(
         self, points: FloatArray, tolerance: Optional[float] = None

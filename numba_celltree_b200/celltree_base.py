@@ -122,7 +122,7 @@ class CellTree2dBase(abc.ABC):
         return float(self._tree.info.default_tolerance)
 
     # ---- fixed-size queries ---------------------------------------------------------------------------------
-    def _locate_points(self, points, tolerance: Optional[float], with_weights: bool):
+    def _locate_points(self, points, tolerance: Optional[float], with_weights: bool, out=None):
         from numba_celltree_b200.cast import cast_vertices
 
         if tolerance is None:
@@ -142,7 +142,10 @@ class CellTree2dBase(abc.ABC):
         else:
             points = cast_vertices(points)
             n = points.shape[0]
-            out = np.empty(n, dtype=IntDType)
+            if out is None:
+                out = np.empty(n, dtype=IntDType)
+            elif not (isinstance(out, np.ndarray) and out.dtype == IntDType and out.shape == (n,) and out.flags.c_contiguous):
+                raise ValueError("out must be a C-contiguous intp array of shape (n_points,)")
             weights = np.empty((n, m), dtype=FloatDType) if with_weights else None
             mem = _lib.CT_MEM_HOST
         _lib.check(lib.ct_locate_points(self._tree.handle, _ptr(points), n, float(tolerance), _ptr(out), _ptr(weights), mem))

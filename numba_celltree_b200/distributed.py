@@ -1,0 +1,131 @@
+"""
+Multi-GPU plumbing for the query path: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch).
+
+The path shards naturally: the tree is REPLICATED (built once on the source rank, broadcast as
+device arrays), queries are split into contiguous ranges of the original query index, fixed-size results need
+no collective, and variable-length results need exactly one all-gather of the per-rank pair totals to turn
+local offsets into global offsets.  Concatenating the per-rank results in rank order reproduces the
+single-GPU (= the reference's) output order.
+
+The host-side logic (shard_range, exchange_totals) is backend-agnostic and is exercised with gloo on CPU in
+tests/test_distributed.py.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of query indices owned by `rank` (sizes differ by at most one, np.array_split style)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def exchange_totals(local_total: int, device=None):
+    """
+    One all-gather of the per-rank result sizes -> (global offset of this rank's first pair, grand total, all totals).
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    mine = torch.tensor([int(local_total)], dtype=torch.int64, device=device)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    totals = [int(t.item()) for t in gathered]
+    return sum(totals[:rank]), sum(totals), totals
+
+
+def globalize_pairs(i_local, lo: int):
+    """Local query indices of a shard -> global query indices (the shard starts at query `lo`)."""
+    return i_local + lo
+
+
+def export_device_arrays(tree, device):
+    """Device copies (torch CUDA tensors) of everything ct_tree_from_arrays needs, in the C-ABI's layouts."""
+    import torch
+
+    from numba_celltree_b200 import _lib
+
+    info = tree._tree.info
+    n, m, n_nodes = int(info.n_elem), int(info.n_max_vert), int(info.n_nodes)
+    arrays = {
+        "vertices": torch.from_numpy(tree.vertices).to(device),
+        "elements": torch.empty((n, m), dtype=torch.int64, device=device),
+        "nodes": torch.empty(n_nodes * 41, dtype=torch.uint8, device=device),
+        "bb_indices": torch.empty(n, dtype=torch.int64, device=device),
+        "bb_coords": torch.empty((n, 4), dtype=torch.float64, device=device),
+    }
+    _lib.check(
+        _lib.load().ct_tree_download(
+            tree._tree.handle, arrays["nodes"].data_ptr(), arrays["bb_indices"].data_ptr(), arrays["bb_coords"].data_ptr(),
+            arrays["elements"].data_ptr(), None, _lib.CT_MEM_DEVICE,
+        )
+    )  # fmt: skip
+    torch.cuda.synchronize(device)
+    meta = {
+        "n_vertex": int(info.n_vertex), "n_elem": n, "n_max_vert": m, "n_nodes": n_nodes, "kind": int(info.kind),
+        "n_buckets": int(info.n_buckets), "cells_per_leaf": int(info.cells_per_leaf), "cls": type(tree).__name__,
+    }  # fmt: skip
+    return meta, arrays
+
+
+def import_device_arrays(meta, arrays):
+    """Build a tree object around device arrays received from another rank (no build kernels run)."""
+    from numba_celltree_b200 import CellTree2d, EdgeCellTree2d, _lib
+    from numba_celltree_b200.celltree_base import DeviceTree
+
+    cls = CellTree2d if meta["cls"] == "CellTree2d" else EdgeCellTree2d
+    handle = ctypes.c_void_p()
+    _lib.check(
+        _lib.load().ct_tree_from_arrays(
+            arrays["vertices"].data_ptr(), meta["n_vertex"], arrays["elements"].data_ptr(), meta["n_elem"], meta["n_max_vert"],
+            meta["kind"], arrays["nodes"].data_ptr(), meta["n_nodes"], arrays["bb_indices"].data_ptr(),
+            arrays["bb_coords"].data_ptr(), meta["cells_per_leaf"], _lib.CT_MEM_DEVICE, ctypes.byref(handle),
+        )
+    )  # fmt: skip
+    tree = cls.__new__(cls)
+    tree._tree = DeviceTree(handle.value)
+    tree.vertices = arrays["vertices"].cpu().numpy()
+    tree.n_buckets = meta["n_buckets"]
+    tree.cells_per_leaf = meta["cells_per_leaf"]
+    if cls is EdgeCellTree2d:
+        tree.edges = arrays["elements"].cpu().numpy()
+    return tree
+
+
+def broadcast_tree(tree, src: int, device):
+    """Replicate the tree of rank `src` on every rank: one broadcast per device array (NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank()
+    if rank == src:
+        meta, arrays = export_device_arrays(tree, device)
+        box = [meta]
+    else:
+        box = [None]
+    dist.broadcast_object_list(box, src=src)
+    meta = box[0]
+    if rank != src:
+        n, m = meta["n_elem"], meta["n_max_vert"]
+        arrays = {
+            "vertices": torch.empty((meta["n_vertex"], 2), dtype=torch.float64, device=device),
+            "elements": torch.empty((n, m), dtype=torch.int64, device=device),
+            "nodes": torch.empty(meta["n_nodes"] * 41, dtype=torch.uint8, device=device),
+            "bb_indices": torch.empty(n, dtype=torch.int64, device=device),
+            "bb_coords": torch.empty((n, 4), dtype=torch.float64, device=device),
+        }
+    for key in ("vertices", "elements", "nodes", "bb_indices", "bb_coords"):
+        dist.broadcast(arrays[key], src=src)
+    torch.cuda.synchronize(device)
+    if rank == src:
+        return tree
+    return import_device_arrays(meta, arrays)
