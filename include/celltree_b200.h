@@ -81,6 +81,10 @@ int ct_set_device(int device);
 int ct_set_stream(void *cuda_stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t ct_launch_count(void);
+/* Morton ordering of point queries (an execution detail, results are unaffected): number of Z-order key bits
+ * the queries are radix-sorted by before the traversal; 0 = keep the caller's order, -1 = automatic (default;
+ * also settable through the environment variable CELLTREE_SORT_BITS). */
+int ct_set_sort_bits(int32_t bits);
 
 /* ---- construction --------------------------------------------------------------------------
  * ct_tree_create replaces the constructor pipeline of CellTree2d.__init__ (celltree.py:74-97) /

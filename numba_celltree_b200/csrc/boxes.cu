@@ -1,0 +1,265 @@
+// boxes.cu -- ct_locate_boxes / ct_locate_faces: count -> scan -> fill traversal of query boxes, then the
+// per-pair geometry (box or polygon clip area, separating axis test) and order-preserving compaction.
+#include "traverse.cuh"
+
+namespace ct {
+
+// ---- box kernels ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(BLOCK) k_locate_boxes(TreeView t, const double *__restrict__ boxes, int64_t n,
+                                                        int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+                                                        int32_t *__restrict__ out_i, int32_t *__restrict__ out_j) {
+    int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (q >= n) return;
+    Box4 box = load_box(boxes, q);
+    if constexpr (FILL) {
+        int64_t base = offsets[q];
+        locate_box(t, box, [&](int k, int bbox_index) {
+            out_i[base + k] = (int32_t)q;
+            out_j[base + k] = bbox_index;
+        });
+    } else {
+        counts[q] = locate_box(t, box, [](int, int) {});
+    }
+}
+
+// ---- pair kernels ------------------------------------------------------------------------------------------------
+CT_DEV void box_polygon(const Box4 &box, Poly<4> &a) {  // copy_box_vertices, geometry_utils.py:513-524
+    a.n = 4;
+    a.x[0] = box.xmin; a.y[0] = box.ymin;
+    a.x[1] = box.xmax; a.y[1] = box.ymin;
+    a.x[2] = box.xmax; a.y[2] = box.ymax;
+    a.x[3] = box.xmin; a.y[3] = box.ymax;
+}
+
+// box_area_of_intersection, algorithms/sutherland_hodgman.py:171-187; flag = area > 0 (celltree.py:183)
+template <int MAXB>
+__global__ void __launch_bounds__(BLOCK) k_box_area(TreeView t, const double *__restrict__ boxes, const int32_t *__restrict__ pi,
+                                                    const int32_t *__restrict__ pj, int64_t n, double *__restrict__ area,
+                                                    int32_t *__restrict__ flag) {
+    int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    Poly<4> a;
+    box_polygon(load_box(boxes, pi[k]), a);
+    Poly<MAXB> b;
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    double ar = polygon_polygon_clip_area<4, MAXB>(a, b);
+    area[k] = ar;
+    flag[k] = ar > 0 ? 1 : 0;
+}
+
+// polygons_intersect, algorithms/separating_axis.py:58-75
+template <int MAXA, int MAXB>
+__global__ void __launch_bounds__(BLOCK) k_sat(TreeView t, const int32_t *__restrict__ qfaces, int qM,
+                                               const double2 *__restrict__ qvertices, const int32_t *__restrict__ pi,
+                                               const int32_t *__restrict__ pj, int64_t n, int32_t *__restrict__ flag) {
+    int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    Poly<MAXA> a;
+    load_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
+    Poly<MAXB> b;
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    flag[k] = (separating_axes<MAXA, MAXB>(a, b) && separating_axes<MAXB, MAXA>(b, a)) ? 1 : 0;
+}
+
+// area_of_intersection, algorithms/sutherland_hodgman.py:151-168; flag = area > 0 (celltree.py:268)
+template <int MAXA, int MAXB>
+__global__ void __launch_bounds__(BLOCK) k_clip_area(TreeView t, const int32_t *__restrict__ qfaces, int qM,
+                                                     const double2 *__restrict__ qvertices, const int32_t *__restrict__ pi,
+                                                     const int32_t *__restrict__ pj, int64_t n, double *__restrict__ area,
+                                                     int32_t *__restrict__ flag) {
+    int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    Poly<MAXA> a;
+    load_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
+    Poly<MAXB> b;
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    double ar = polygon_polygon_clip_area<MAXA, MAXB>(a, b);
+    area[k] = ar;
+    flag[k] = ar > 0 ? 1 : 0;
+}
+
+// count -> scan -> fill for boxes already on the device; result pairs in r (int32 i, j)
+static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64_t n, ct_result *r, cudaStream_t s) {
+    TreeView v = tree->view();
+    Scratch<int32_t> counts;
+    Scratch<int64_t> offsets;
+    CT_CHECK(counts.alloc(n + 1, s));
+    CT_CHECK(offsets.alloc(n + 1, s));
+    CT_CUDA(cudaMemsetAsync(counts.p + n, 0, sizeof(int32_t), s));
+    int64_t total = 0;
+    if (n > 0) {
+        k_locate_boxes<false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr);
+        CT_LAUNCH_CHECK();
+    }
+    CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
+    CT_CHECK(dalloc(&r->i, total, s));
+    CT_CHECK(dalloc(&r->j, total, s));
+    r->size = total;
+    r->width = 0;
+    if (n > 0 && total > 0) {
+        k_locate_boxes<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j);
+        CT_LAUNCH_CHECK();
+    }
+    return CT_OK;
+}
+
+template <int MAXB>
+static int launch_box_area(const ct_tree *tree, const double *d_boxes, ct_result *r, double *area, int32_t *flag, cudaStream_t s) {
+    k_box_area<MAXB><<<grid_for(r->size, BLOCK), BLOCK, 0, s>>>(tree->view(), d_boxes, r->i, r->j, r->size, area, flag);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+template <int MAXA, int MAXB>
+static int launch_sat(const ct_tree *tree, const int32_t *qf, int qM, const double2 *qv, ct_result *r, int32_t *flag, cudaStream_t s) {
+    k_sat<MAXA, MAXB><<<grid_for(r->size, BLOCK), BLOCK, 0, s>>>(tree->view(), qf, qM, qv, r->i, r->j, r->size, flag);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+template <int MAXA, int MAXB>
+static int launch_clip(const ct_tree *tree, const int32_t *qf, int qM, const double2 *qv, ct_result *r, double *area, int32_t *flag,
+                       cudaStream_t s) {
+    k_clip_area<MAXA, MAXB><<<grid_for(r->size, BLOCK), BLOCK, 0, s>>>(tree->view(), qf, qM, qv, r->i, r->j, r->size, area, flag);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
+static inline int bound_of(int M) { return M == 3 ? 3 : (M == 4 ? 4 : 32); }
+
+#define CT_DISPATCH_PAIR(FN, MA, MB, ...)                                   \
+    do {                                                                    \
+        int _a = bound_of(MA), _b = bound_of(MB);                           \
+        if (_a == 3 && _b == 3) CT_CHECK((FN<3, 3>(__VA_ARGS__)));          \
+        else if (_a == 3 && _b == 4) CT_CHECK((FN<3, 4>(__VA_ARGS__)));     \
+        else if (_a == 3) CT_CHECK((FN<3, 32>(__VA_ARGS__)));               \
+        else if (_a == 4 && _b == 3) CT_CHECK((FN<4, 3>(__VA_ARGS__)));     \
+        else if (_a == 4 && _b == 4) CT_CHECK((FN<4, 4>(__VA_ARGS__)));     \
+        else if (_a == 4) CT_CHECK((FN<4, 32>(__VA_ARGS__)));               \
+        else if (_b == 3) CT_CHECK((FN<32, 3>(__VA_ARGS__)));               \
+        else if (_b == 4) CT_CHECK((FN<32, 4>(__VA_ARGS__)));               \
+        else CT_CHECK((FN<32, 32>(__VA_ARGS__)));                           \
+    } while (0)
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t n, int32_t with_area, int32_t mem, ct_result **out) {
+    if (!tree || !out || n < 0 || (n > 0 && !boxes)) {
+        set_error("ct_locate_boxes: null argument");
+        return CT_ERR_VALUE;
+    }
+    if (tree->kind != CT_KIND_FACES && with_area) {
+        set_error("ct_locate_boxes: areas need a face tree");
+        return CT_ERR_VALUE;
+    }
+    CT_CHECK(check_depth(tree));
+    CT_CUDA(cudaSetDevice(tree->device));
+    cudaStream_t s = current_stream();
+    DevIn<double> d_boxes;
+    CT_CHECK(d_boxes.init(boxes, (size_t)n * 4, mem, s));
+    ct_result *r = new ct_result();
+    int status = locate_boxes_device(tree, d_boxes.p, n, r, s);
+    if (status == CT_OK && with_area) {
+        auto stage = [&]() -> int {
+            Scratch<double> area;
+            Scratch<int32_t> flag;
+            CT_CHECK(area.alloc(r->size, s));
+            CT_CHECK(flag.alloc(r->size, s));
+            if (r->size > 0) {
+                int b = tree->M == 3 ? 3 : (tree->M == 4 ? 4 : 32);
+                if (b == 3) CT_CHECK(launch_box_area<3>(tree, d_boxes.p, r, area.p, flag.p, s));
+                else if (b == 4) CT_CHECK(launch_box_area<4>(tree, d_boxes.p, r, area.p, flag.p, s));
+                else CT_CHECK(launch_box_area<32>(tree, d_boxes.p, r, area.p, flag.p, s));
+            }
+            r->payload = area.release();
+            r->width = 1;
+            return compact_result(r, flag.p, true, s);
+        };
+        status = stage();
+    }
+    if (status == CT_OK) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            set_error(std::string("ct_locate_boxes: ") + cudaGetErrorString(e));
+            status = CT_ERR_CUDA;
+        }
+    }
+    if (status != CT_OK) {
+        ct_result_free(r);
+        return status;
+    }
+    *out = r;
+    return CT_OK;
+}
+
+extern "C" int ct_locate_faces(const ct_tree *tree, const double *vertices, int64_t n_vertex, int64_t *faces, int64_t n_face,
+                               int32_t n_max_vert, int32_t with_area, int32_t mem, ct_result **out) {
+    if (!tree || !out || n_face < 0 || n_vertex < 0 || (n_face > 0 && (!faces || !vertices))) {
+        set_error("ct_locate_faces: null argument");
+        return CT_ERR_VALUE;
+    }
+    if (tree->kind != CT_KIND_FACES) {
+        set_error("ct_locate_faces: needs a face tree");
+        return CT_ERR_VALUE;
+    }
+    if (n_max_vert < 3 || n_max_vert > MAX_N_VERTEX) {
+        set_error("ct_locate_faces: faces must have 3..32 columns");
+        return CT_ERR_VALUE;
+    }
+    CT_CHECK(check_depth(tree));
+    CT_CUDA(cudaSetDevice(tree->device));
+    cudaStream_t s = current_stream();
+    const int qM = n_max_vert;
+    DevIn<double> d_qv;
+    CT_CHECK(d_qv.init(vertices, (size_t)n_vertex * 2, mem, s));
+    DevIn<int64_t> d_qf64;
+    CT_CHECK(d_qf64.init(faces, (size_t)n_face * qM, mem, s));
+    Scratch<int32_t> qf;
+    Scratch<double> qbb;
+    CT_CHECK(qf.alloc((size_t)n_face * qM, s));
+    CT_CHECK(qbb.alloc((size_t)n_face * 4, s));
+    const double2 *qv = reinterpret_cast<const double2 *>(d_qv.p);
+    ct_result *r = new ct_result();
+    auto body = [&]() -> int {
+        if (n_face > 0) {
+            CT_CHECK(launch_narrow(d_qf64.p, n_face * qM, qf.p, s));
+            // counter_clockwise on the query faces, in place as the reference does (celltree.py:212)
+            CT_CHECK(launch_counter_clockwise(qv, qf.p, n_face, qM, s));
+            int64_t *faces_dev = const_cast<int64_t *>(d_qf64.p);
+            CT_CHECK(launch_widen(qf.p, n_face * qM, faces_dev, s));
+            if (mem == CT_MEM_HOST)
+                CT_CUDA(cudaMemcpyAsync(faces, faces_dev, (size_t)n_face * qM * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CT_CHECK(launch_face_bboxes(qv, qf.p, n_face, qM, qbb.p, s));
+        }
+        CT_CHECK(locate_boxes_device(tree, qbb.p, n_face, r, s));
+        {
+            Scratch<int32_t> flag;
+            CT_CHECK(flag.alloc(r->size, s));
+            if (r->size > 0) CT_DISPATCH_PAIR(launch_sat, qM, tree->M, tree, qf.p, qM, qv, r, flag.p, s);
+            CT_CHECK(compact_result(r, flag.p, false, s));
+        }
+        if (with_area) {
+            Scratch<double> area;
+            Scratch<int32_t> flag;
+            CT_CHECK(area.alloc(r->size, s));
+            CT_CHECK(flag.alloc(r->size, s));
+            if (r->size > 0) CT_DISPATCH_PAIR(launch_clip, qM, tree->M, tree, qf.p, qM, qv, r, area.p, flag.p, s);
+            r->payload = area.release();
+            r->width = 1;
+            CT_CHECK(compact_result(r, flag.p, true, s));
+        }
+        CT_CUDA(cudaStreamSynchronize(s));
+        return CT_OK;
+    };
+    int status = body();
+    if (status != CT_OK) {
+        ct_result_free(r);
+        return status;
+    }
+    *out = r;
+    return CT_OK;
+}
+

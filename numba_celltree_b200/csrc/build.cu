@@ -27,6 +27,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "geometry.cuh"
@@ -664,7 +665,15 @@ static int64_t pessimistic_n_nodes(int64_t n_elements) {  // creation.py:216-230
     return n_nodes + 1;
 }
 
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int build_tree(ct_tree *tree, cudaStream_t s) {
+    const bool debug = getenv("CELLTREE_DEBUG") != nullptr;
+    double t_start = now_ms();
     const int64_t n = tree->n_elem;
     const int nb = tree->n_buckets, cpl = tree->cells_per_leaf;
     const int64_t cap_nodes = pessimistic_n_nodes(n) + 2;
@@ -736,6 +745,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         CT_CUDA(cudaStreamSynchronize(s));  // the host temporaries above go out of scope
     }
 
+    double t_alloc = now_ms();
     BuildState st;
     st.bb = tree->bb_coords;
     st.bkt = bkt.p;
@@ -802,6 +812,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         }
     }
     wave_start.push_back(node_count);
+    double t_waves = now_ms();
 
     // renumber: creation order -> the reference's depth-first numbering
     CT_CHECK(splits.alloc(node_count, s));
@@ -841,6 +852,9 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     CT_CUDA(cudaStreamSynchronize(s));
     tree->n_nodes = node_count;
     tree->depth = h_level;
+    if (debug)
+        fprintf(stderr, "[celltree] build n=%lld: alloc %.2f ms, %d waves %.2f ms, renumber %.2f ms\n", (long long)n,
+                t_alloc - t_start, (int)wave_start.size() - 2, t_waves - t_alloc, now_ms() - t_waves);
     return CT_OK;
 }
 

@@ -1,4 +1,4 @@
-// common.cuh -- device tree layout, error plumbing and small helpers shared by build.cu / query.cu.
+// common.cuh -- device tree layout, error plumbing and host helpers shared by the translation units.
 //
 // Everything in csrc/ is compiled with -fmad=false: the reference (Numba/LLVM) emits no fused
 // multiply-adds, and bucket membership / on-edge decisions / pair lists depend on the last bit.
@@ -113,6 +113,65 @@ inline int grid_for(int64_t n, int block) {
 }
 
 // ---- the device tree ---------------------------------------------------------------------------------
+}  // namespace ct
+struct ct_tree;
+struct ct_result;
+namespace ct {
+// ---- shared host helpers (lib.cu / build.cu) --------------------------------------------------------------
+constexpr int BLOCK = 128;  // query kernels: one query (or pair) per thread
+
+// Device view of a caller array: for CT_MEM_HOST a stream-ordered scratch copy, else the pointer itself.
+template <typename T>
+struct DevIn {
+    Scratch<T> owned;
+    const T *p = nullptr;
+    int init(const T *src, size_t count, int mem, cudaStream_t s) {
+        if (mem == CT_MEM_DEVICE) {
+            p = src;
+            return CT_OK;
+        }
+        CT_CHECK(owned.alloc(count, s));
+        if (count) CT_CUDA(cudaMemcpyAsync(owned.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        p = owned.p;
+        return CT_OK;
+    }
+};
+
+template <typename T>
+struct DevOut {
+    Scratch<T> owned;
+    T *p = nullptr;
+    T *host = nullptr;
+    size_t count = 0;
+    int init(T *dst, size_t n, int mem, cudaStream_t s) {
+        count = n;
+        if (dst == nullptr) return CT_OK;
+        if (mem == CT_MEM_DEVICE) {
+            p = dst;
+            return CT_OK;
+        }
+        host = dst;
+        CT_CHECK(owned.alloc(n, s));
+        p = owned.p;
+        return CT_OK;
+    }
+    int finish(cudaStream_t s) {
+        if (host && count) CT_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+        return CT_OK;
+    }
+};
+
+
+int check_depth(const ct_tree *tree);
+int sort_bits_override();  // -1 = automatic
+// exclusive scan of int32 counts[0..n] (counts[n] must be 0) into int64 offsets[0..n]; *total = offsets[n]
+int scan_counts(const int32_t *counts, int64_t n, int64_t *offsets, int64_t *total, cudaStream_t s);
+// keep the flagged pairs of a result, order preserved
+int compact_result(ct_result *r, const int32_t *flag, bool keep_payload, cudaStream_t s);
+int launch_widen(const int32_t *in, int64_t n, int64_t *out, cudaStream_t s);
+int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s);
+int launch_counter_clockwise(const double2 *vertices, int32_t *faces, int64_t n_face, int M, cudaStream_t s);
+int launch_face_bboxes(const double2 *vertices, const int32_t *faces, int64_t n_face, int M, double *bb, cudaStream_t s);
 }  // namespace ct
 
 struct ct_tree {

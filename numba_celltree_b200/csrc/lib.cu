@@ -1,0 +1,177 @@
+// lib.cu -- library state (error string, stream, launch counter), the helpers shared by the query
+// translation units (scan of per-query counts, order-preserving compaction) and the result / misc entry points.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "traverse.cuh"
+
+namespace ct {
+
+// ---- library state -----------------------------------------------------------------------------------
+static thread_local std::string g_error;
+static thread_local cudaStream_t g_stream = 0;
+static int64_t g_launches = 0;
+
+void set_error(const std::string &msg) { g_error = msg; }
+cudaStream_t current_stream() { return g_stream; }
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+
+static int g_sort_bits = -1;
+int sort_bits_override() {
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        const char *e = getenv("CELLTREE_SORT_BITS");
+        if (e) g_sort_bits = atoi(e);
+    }
+    return g_sort_bits;
+}
+
+int check_depth(const ct_tree *tree) {
+    if (tree->depth > STACK_CAP) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "tree has %d levels; the traversal stack holds %d", tree->depth, STACK_CAP);
+        set_error(buf);
+        return CT_ERR_DEPTH;
+    }
+    return CT_OK;
+}
+
+// keep the flagged pairs, order preserved (the NumPy boolean masks of celltree.py:183-184, 226, 268-269)
+__global__ void __launch_bounds__(256) k_compact(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t n,
+                                                 const int32_t *__restrict__ in_i, const int32_t *__restrict__ in_j,
+                                                 const double *__restrict__ in_p, int32_t *__restrict__ out_i,
+                                                 int32_t *__restrict__ out_j, double *__restrict__ out_p) {
+    int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n || !flag[k]) return;
+    int64_t o = pos[k];
+    out_i[o] = in_i[k];
+    out_j[o] = in_j[k];
+    if (in_p) out_p[o] = in_p[k];
+}
+
+// exclusive scan of int32 counts into int64 offsets[n + 1]; total returned through the last element
+int scan_counts(const int32_t *counts, int64_t n, int64_t *offsets, int64_t *total, cudaStream_t s) {
+    // offsets[0..n) = exclusive sum; offsets[n] = total.  Scan n + 1 items (counts has a zero sentinel at [n]).
+    size_t bytes = 0;
+    auto in = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>(counts, cub::CastOp<int64_t>());
+    CT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, offsets, n + 1, s));
+    Scratch<char> tmp;
+    CT_CHECK(tmp.alloc(bytes, s));
+    CT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, offsets, n + 1, s));
+    count_launch(2);
+    CT_CUDA(cudaMemcpyAsync(total, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    return CT_OK;
+}
+
+// Replace (i, j, payload) of `r` by the flagged subset.
+int compact_result(ct_result *r, const int32_t *flag, bool keep_payload, cudaStream_t s) {
+    int64_t n = r->size;
+    Scratch<int64_t> pos;
+    CT_CHECK(pos.alloc(n + 1, s));
+    int64_t total = 0;
+    // flag has n entries; scan n+1 needs a sentinel: scan n items and add the last flag on the host side
+    {
+        size_t bytes = 0;
+        auto in = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>(flag, cub::CastOp<int64_t>());
+        CT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, pos.p, n, s));
+        Scratch<char> tmp;
+        CT_CHECK(tmp.alloc(bytes, s));
+        if (n > 0) {
+            CT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, pos.p, n, s));
+            count_launch(2);
+            int64_t last_pos = 0;
+            int32_t last_flag = 0;
+            CT_CUDA(cudaMemcpyAsync(&last_pos, pos.p + n - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CT_CUDA(cudaMemcpyAsync(&last_flag, flag + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CT_CUDA(cudaStreamSynchronize(s));
+            total = last_pos + last_flag;
+        }
+    }
+    int32_t *ni = nullptr, *nj = nullptr;
+    double *np_ = nullptr;
+    CT_CHECK(dalloc(&ni, total, s));
+    CT_CHECK(dalloc(&nj, total, s));
+    if (keep_payload) CT_CHECK(dalloc(&np_, total, s));
+    if (n > 0) {
+        k_compact<<<grid_for(n, 256), 256, 0, s>>>(flag, pos.p, n, r->i, r->j, keep_payload ? r->payload : nullptr, ni, nj, np_);
+        CT_LAUNCH_CHECK();
+    }
+    dfree(r->i, s);
+    dfree(r->j, s);
+    dfree(r->payload, s);
+    r->i = ni;
+    r->j = nj;
+    r->payload = np_;
+    r->width = keep_payload ? 1 : 0;
+    r->size = total;
+    return CT_OK;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" int64_t ct_result_size(const ct_result *r) { return r ? r->size : 0; }
+extern "C" int32_t ct_result_payload_width(const ct_result *r) { return r ? r->width : 0; }
+
+extern "C" int ct_result_fetch(const ct_result *r, int64_t *i, int64_t *j, double *payload, int32_t mem) {
+    if (!r) {
+        set_error("ct_result_fetch: null result");
+        return CT_ERR_VALUE;
+    }
+    cudaStream_t s = current_stream();
+    int64_t n = r->size;
+    if (n == 0) return CT_OK;
+    DevOut<int64_t> oi, oj;
+    CT_CHECK(oi.init(i, n, mem, s));
+    CT_CHECK(oj.init(j, n, mem, s));
+    if (i) {
+        CT_CHECK(launch_widen(r->i, n, oi.p, s));
+        CT_CHECK(oi.finish(s));
+    }
+    if (j) {
+        CT_CHECK(launch_widen(r->j, n, oj.p, s));
+        CT_CHECK(oj.finish(s));
+    }
+    if (payload && r->width > 0)
+        CT_CUDA(cudaMemcpyAsync(payload, r->payload, (size_t)n * r->width * sizeof(double),
+                                mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    return CT_OK;
+}
+
+extern "C" void ct_result_free(ct_result *r) {
+    if (!r) return;
+    cudaStream_t s = current_stream();
+    dfree(r->i, s);
+    dfree(r->j, s);
+    dfree(r->payload, s);
+    delete r;
+}
+
+extern "C" const char *ct_last_error(void) { return g_error.c_str(); }
+
+extern "C" int ct_device_count(int *count) {
+    CT_CUDA(cudaGetDeviceCount(count));
+    return CT_OK;
+}
+
+extern "C" int ct_set_device(int device) {
+    CT_CUDA(cudaSetDevice(device));
+    return CT_OK;
+}
+
+extern "C" int ct_set_stream(void *cuda_stream) {
+    g_stream = (cudaStream_t)cuda_stream;
+    return CT_OK;
+}
+
+extern "C" int64_t ct_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int ct_set_sort_bits(int32_t bits) {
+    (void)sort_bits_override();
+    g_sort_bits = bits;
+    return CT_OK;
+}

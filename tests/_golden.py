@@ -14,8 +14,8 @@ import numpy as np
 GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 RTOL = 1e-12
 BUILD_PARAMS = [(4, 2), (2, 1), (2, 2), (8, 3), (3, 1), (16, 4)]
-FACE_CASES = ["disk_5_5", "triangles_538", "voronoi_74", "quads_48_40_mixed", "delaunay_3000", "duplicates"]
-EDGE_CASES = ["network_demo", "network_800", "network_grid"]
+FACE_CASES = ["disk_5_5", "triangles_538", "voronoi_74", "quads_48_40_mixed", "delaunay_3000", "duplicates", "lattice_faces"]
+EDGE_CASES = ["network_demo", "network_800", "network_grid", "lattice_network"]
 
 
 def load(name):
@@ -68,6 +68,10 @@ def check_face_tree_points(CellTree2d, name):
     fi, w = t.compute_barycentric_weights(pts)
     assert np.array_equal(fi, g["locate_points"])
     assert_close(w, g["weights"], f"{name} barycentric weights")
+    if "weights_tol1" in g:
+        fi, w = t.compute_barycentric_weights(pts, tolerance=float(g["tol1"]))
+        assert np.array_equal(fi, g["locate_points_tol1"])
+        assert_close(w, g["weights_tol1"], f"{name} barycentric weights tol1")
 
 
 def check_face_tree_boxes(CellTree2d, name):

@@ -204,5 +204,106 @@ def main():
     edge_tree_case("network_grid", gv * 100.0 + 5000.0, ge.astype(np.int64), rng, n_query=200)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("CELLTREE_GOLDEN_ONLY", "all") == "all":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Degenerate lattice cases: every coordinate on a (half-)integer lattice, so that queries run through
+# vertices, along cell edges, touch boxes exactly and overlap collinearly -- the branches that random
+# inputs never reach.  Expected outputs come from the reference, as everywhere else in this file.
+def lattice_cases():
+    # a 4 x 3 block of unit cells: quads, some split into two triangles, one pentagon with a hanging node
+    xs, ys = np.meshgrid(np.arange(5.0), np.arange(4.0), indexing="xy")
+    vertices = np.column_stack((xs.ravel(), ys.ravel()))
+    vertices = np.vstack([vertices, [[2.5, 0.0]]])  # vertex 20: hanging node on the bottom edge of cell (2, 0)
+    vid = lambda i, j: j * 5 + i  # noqa: E731
+    faces = []
+    for j in range(3):
+        for i in range(4):
+            a, b, c, d = vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)
+            if (i, j) == (2, 0):
+                faces.append([a, 20, b, c, d])  # pentagon with a collinear (hanging) vertex
+            elif (i + j) % 3 == 0:
+                faces.append([a, b, c, -1, -1])
+                faces.append([a, c, d, -1, -1])
+            elif (i + j) % 3 == 1:
+                faces.append([d, c, b, a, -1])  # clockwise quad: counter_clockwise must flip it
+            else:
+                faces.append([a, b, c, d, -1])
+    faces = np.array(faces, dtype=np.int64)
+    out = {"vertices": vertices, "faces": faces, "fill_value": np.int64(-1)}
+    for nb_, cpl in BUILD_PARAMS:
+        t = CellTree2d(vertices, faces, -1, n_buckets=nb_, cells_per_leaf=cpl)
+        tree_arrays(t, f"b{nb_}_c{cpl}_", out)
+    tree = CellTree2d(vertices, faces, -1)
+    out["faces_ccw"] = tree.faces
+    out["bb_distances"] = tree.bb_distances
+    hx, hy = np.meshgrid(np.arange(-1.0, 5.01, 0.5), np.arange(-1.0, 4.01, 0.5), indexing="xy")
+    points = np.column_stack((hx.ravel(), hy.ravel()))
+    eps = np.array([[1e-13, 0.0], [0.0, -1e-13], [3e-16, 3e-16], [-1e-9, 1e-9]])
+    points = np.concatenate([points] + [points + e for e in eps])
+    out["points"] = points
+    out["locate_points"] = tree.locate_points(points)
+    for k, tol in enumerate((1e-9, 1e-3)):
+        out[f"locate_points_tol{k}"] = tree.locate_points(points, tolerance=tol)
+        out[f"tol{k}"] = np.float64(tol)
+    _, out["weights"] = tree.compute_barycentric_weights(points)
+    _, out["weights_tol1"] = tree.compute_barycentric_weights(points, tolerance=1e-3)
+    c = np.arange(-1.0, 5.01, 1.0)
+    boxes = np.array([[x0, x1, y0, y1] for x0 in c for x1 in c if x1 > x0 for y0 in c[:-1] for y1 in c[:-1] if y1 > y0])
+    boxes = np.concatenate([boxes, boxes[::7] + [0.5, 0.5, 0.5, 0.5], [[1.0, 1.0, 0.0, 2.0]]])
+    out["boxes"] = boxes
+    out["locate_boxes_i"], out["locate_boxes_j"] = tree.locate_boxes(boxes)
+    out["intersect_boxes_i"], out["intersect_boxes_j"], out["intersect_boxes_area"] = tree.intersect_boxes(boxes)
+    px, py = np.meshgrid(np.arange(-0.5, 4.51, 0.5), np.arange(-0.5, 3.51, 0.5), indexing="xy")
+    lp = np.column_stack((px.ravel(), py.ravel()))
+    ia, ib = np.meshgrid(np.arange(len(lp)), np.arange(len(lp)), indexing="ij")
+    sel = (ia.ravel() * 7 + ib.ravel() * 3) % 5 == 0  # every fifth ordered pair, degenerate ones included
+    edges = np.stack((lp[ia.ravel()[sel]], lp[ib.ravel()[sel]]), axis=1)
+    out["edges"] = edges
+    out["intersect_edges_i"], out["intersect_edges_j"], out["intersect_edges_xy"] = tree.intersect_edges(edges)
+    # the same mesh shifted by (half-)integer offsets: shared edges, shared vertices, exact containment
+    ov = np.concatenate([vertices + s for s in ([0.0, 0.0], [0.5, 0.0], [1.0, 1.0], [0.5, 0.5], [4.0, 0.0], [-1.0, 3.0])])
+    of = np.concatenate([np.where(faces == -1, -1, faces + k * len(vertices)) for k in range(6)])
+    out["other_vertices"], out["other_faces"], out["other_fill"] = ov, of, np.int64(-1)
+    out["intersect_faces_i"], out["intersect_faces_j"], out["intersect_faces_area"] = tree.intersect_faces(ov, of, -1)
+    li, lj = tree.locate_faces(ov.copy(), of.copy())
+    out["locate_faces_i"], out["locate_faces_j"] = li, lj
+    si, sj, sa = tree.intersect_faces(vertices, faces, -1)
+    out["self_faces_i"], out["self_faces_j"], out["self_faces_area"] = si, sj, sa
+    np.savez_compressed(HERE / "lattice_faces.npz", **out)
+    print("lattice_faces", len(points), len(boxes), len(edges), len(out["intersect_edges_i"]), len(out["intersect_faces_i"]))
+
+    # lattice network for EdgeCellTree2d: unit horizontal / vertical / diagonal edges, one zero-length edge
+    nv = np.column_stack((xs.ravel(), ys.ravel()))
+    ne = []
+    for j in range(4):
+        for i in range(5):
+            if i < 4 and (i + j) % 2 == 0:
+                ne.append([vid(i, j), vid(i + 1, j)])
+            if j < 3 and (i + 2 * j) % 3 != 1:
+                ne.append([vid(i, j), vid(i, j + 1)])
+            if i < 4 and j < 3 and (i * j) % 2 == 1:
+                ne.append([vid(i, j), vid(i + 1, j + 1)])
+    ne.append([7, 7])
+    ne = np.array(ne, dtype=np.int64)
+    out = {"vertices": nv, "edges": ne}
+    for nb_, cpl in BUILD_PARAMS:
+        t = EdgeCellTree2d(nv, ne, n_buckets=nb_, cells_per_leaf=cpl)
+        tree_arrays(t, f"b{nb_}_c{cpl}_", out)
+    tree = EdgeCellTree2d(nv, ne)
+    out["bb_distances"] = tree.bb_distances
+    out["points"] = points
+    out["locate_points"] = tree.locate_points(points)
+    for k, tol in enumerate((1e-9, 1e-3)):
+        out[f"locate_points_tol{k}"] = tree.locate_points(points, tolerance=tol)
+        out[f"tol{k}"] = np.float64(tol)
+    out["query_edges"] = edges
+    out["intersect_edges_i"], out["intersect_edges_j"], out["intersect_edges_xy"] = tree.intersect_edges(edges)
+    np.savez_compressed(HERE / "lattice_network.npz", **out)
+    print("lattice_network", len(ne), len(out["intersect_edges_i"]))
+
+
+if __name__ == "__main__" and os.environ.get("CELLTREE_GOLDEN_ONLY", "all") in ("all", "lattice"):
+    lattice_cases()

@@ -1,0 +1,249 @@
+"""
+CUDA path vs the CPU oracle on seeded random inputs at sizes the oracle finishes in seconds, plus the edge
+cases the domain has: empty query sets, a single cell, everything outside, NaN coordinates, trees deeper than
+the traversal stack, device-resident inputs, and Morton ordering on/off.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+from numba_celltree_b200.synthetic import c3_boxes, c4_edges, delaunay_mesh, quad_mesh
+from tests._golden import RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import numba_celltree_b200
+
+    return numba_celltree_b200
+
+
+@pytest.fixture(scope="module")
+def delaunay_pair(pkg):
+    vertices, faces = delaunay_mesh(100_000, seed=1234)
+    return pkg.CellTree2d(vertices, faces, -1), oracle.CellTree2d(vertices, faces, -1), vertices, faces
+
+
+def assert_same_tree(tree, ref):
+    for field in ("child", "Lmax", "Rmin", "ptr", "size", "dim"):
+        assert np.array_equal(tree.nodes[field], ref.nodes[field]), field
+    assert np.array_equal(tree.bb_indices, ref.bb_indices)
+    assert np.array_equal(tree.bb_coords, ref.bb_coords)
+    assert np.array_equal(tree.bbox, ref.bbox)
+
+
+def test_build_delaunay_bit_exact(delaunay_pair):
+    tree, ref, _, _ = delaunay_pair
+    assert_same_tree(tree, ref)
+    assert np.array_equal(tree.faces, ref.faces)
+
+
+@pytest.mark.parametrize("n_buckets,cells_per_leaf", [(2, 1), (3, 2), (8, 4), (13, 1), (64, 2), (100, 3)])
+def test_build_parameters_bit_exact(pkg, n_buckets, cells_per_leaf):
+    vertices, faces = delaunay_mesh(20_000, seed=n_buckets)
+    tree = pkg.CellTree2d(vertices, faces, -1, n_buckets=n_buckets, cells_per_leaf=cells_per_leaf)
+    ref = oracle.CellTree2d(vertices, faces, -1, n_buckets=n_buckets, cells_per_leaf=cells_per_leaf)
+    assert_same_tree(tree, ref)
+
+
+def test_build_structured_quads_bit_exact(pkg):
+    vertices, faces = quad_mesh(512, 384)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    assert_same_tree(tree, ref)
+    pts = np.random.default_rng(5).uniform(-0.05, 1.05, (500_000, 2))
+    idx, w = tree.compute_barycentric_weights(pts)
+    ridx, rw = ref.compute_barycentric_weights(pts)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(w, rw)
+
+
+def test_points_and_weights(delaunay_pair):
+    tree, ref, _, _ = delaunay_pair
+    pts = np.random.default_rng(1).uniform(-0.02, 1.02, (2_000_000, 2))
+    for tol in (None, 1e-7):
+        idx, w = tree.compute_barycentric_weights(pts, tolerance=tol)
+        ridx, rw = ref.compute_barycentric_weights(pts, tolerance=tol)
+        assert np.array_equal(idx, ridx)
+        np.testing.assert_allclose(w, rw, rtol=RTOL, atol=0)
+        assert np.array_equal(w, rw)
+
+
+def test_morton_ordering_is_invisible(pkg, delaunay_pair):
+    from numba_celltree_b200 import _lib
+
+    tree, _, _, _ = delaunay_pair
+    pts = np.random.default_rng(2).uniform(0, 1, (1_500_000, 2))
+    lib = _lib.load()
+    results = []
+    try:
+        for bits in (0, 8, 16, 24, 32):
+            lib.ct_set_sort_bits(bits)
+            results.append(tree.compute_barycentric_weights(pts))
+    finally:
+        lib.ct_set_sort_bits(-1)
+    for idx, w in results[1:]:
+        assert np.array_equal(idx, results[0][0])
+        assert np.array_equal(w, results[0][1])
+
+
+def test_device_resident_inputs_match_host(delaunay_pair):
+    torch = pytest.importorskip("torch")
+    tree, _, _, faces = delaunay_pair
+    pts = np.random.default_rng(3).uniform(0, 1, (300_000, 2))
+    idx, w = tree.compute_barycentric_weights(pts)
+    d_idx, d_w = tree.compute_barycentric_weights(torch.from_numpy(pts).cuda())
+    assert d_idx.is_cuda and d_w.is_cuda
+    assert np.array_equal(d_idx.cpu().numpy(), idx) and np.array_equal(d_w.cpu().numpy(), w)
+    boxes = c3_boxes(len(faces), 50_000)
+    i, j, a = tree.intersect_boxes(boxes)
+    di, dj, da = tree.intersect_boxes(torch.from_numpy(boxes).cuda())
+    assert np.array_equal(di.cpu().numpy(), i) and np.array_equal(dj.cpu().numpy(), j) and np.array_equal(da.cpu().numpy(), a)
+    edges = c4_edges(len(faces), 20_000)
+    i, j, xy = tree.intersect_edges(edges)
+    di, dj, dxy = tree.intersect_edges(torch.from_numpy(edges).cuda())
+    assert np.array_equal(di.cpu().numpy(), i) and np.array_equal(dj.cpu().numpy(), j)
+    assert np.array_equal(dxy.cpu().numpy(), xy, equal_nan=True)
+
+
+def test_boxes(delaunay_pair):
+    tree, ref, _, faces = delaunay_pair
+    boxes = c3_boxes(len(faces), 300_000)
+    i, j = tree.locate_boxes(boxes)
+    ri, rj = ref.locate_boxes(boxes)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    i, j, a = tree.intersect_boxes(boxes)
+    ri, rj, ra = ref.intersect_boxes(boxes)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    np.testing.assert_allclose(a, ra, rtol=RTOL, atol=0)
+    assert np.array_equal(a, ra)
+
+
+def test_edges(delaunay_pair):
+    tree, ref, _, faces = delaunay_pair
+    edges = c4_edges(len(faces), 100_000)
+    i, j, xy = tree.intersect_edges(edges)
+    ri, rj, rxy = ref.intersect_edges(edges)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    np.testing.assert_allclose(xy, rxy, rtol=RTOL, atol=0)
+    assert np.array_equal(xy, rxy, equal_nan=True)
+
+
+def test_faces_and_self_intersection(delaunay_pair):
+    tree, ref, vertices, faces = delaunay_pair
+    qv, qf = quad_mesh(150, 150)
+    i, j, a = tree.intersect_faces(qv, qf, -1)
+    ri, rj, ra = ref.intersect_faces(qv, qf, -1)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    np.testing.assert_allclose(a, ra, rtol=RTOL, atol=0)
+    # the total overlap equals the area of the triangulated convex hull (size-independent property)
+    tri = vertices[faces]
+    hull_area = 0.5 * np.abs(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])).sum()
+    assert abs(a.sum() - hull_area) < 1e-9
+    # the mesh against itself: sliver pairs at rounding-noise level must match too
+    i, j, a = tree.intersect_faces(vertices, faces, -1)
+    ri, rj, ra = ref.intersect_faces(vertices, faces, -1)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    assert np.array_equal(a, ra)
+
+
+def test_edge_network(pkg):
+    from numba_celltree_b200.synthetic import random_network
+
+    vertices, edges = random_network(50_000, seed=9)
+    tree = pkg.EdgeCellTree2d(vertices, edges)
+    ref = oracle.EdgeCellTree2d(vertices, edges)
+    assert_same_tree(tree, ref)
+    rng = np.random.default_rng(4)
+    p, q = vertices[edges[:, 0]], vertices[edges[:, 1]]
+    on = p + rng.uniform(0, 1, (len(edges), 1)) * (q - p)
+    pts = np.concatenate([on, on + rng.normal(0, 1e-9, on.shape), rng.uniform(vertices.min(0), vertices.max(0), (100_000, 2))])
+    for tol in (None, 1e-6):
+        assert np.array_equal(tree.locate_points(pts, tolerance=tol), ref.locate_points(pts, tolerance=tol))
+    a0 = rng.uniform(vertices.min(0), vertices.max(0), (50_000, 2))
+    qe = np.stack((a0, a0 + rng.normal(0, 3.0, a0.shape)), axis=1)
+    i, j, xy = tree.intersect_edges(qe)
+    ri, rj, rxy = ref.intersect_edges(qe)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    assert np.array_equal(xy, rxy, equal_nan=True)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+def test_empty_query_sets(delaunay_pair):
+    tree, _, _, _ = delaunay_pair
+    assert tree.locate_points(np.empty((0, 2))).shape == (0,)
+    idx, w = tree.compute_barycentric_weights(np.empty((0, 2)))
+    assert idx.shape == (0,) and w.shape == (0, 3)
+    i, j = tree.locate_boxes(np.empty((0, 4)))
+    assert i.shape == (0,) and j.shape == (0,) and i.dtype == np.intp
+    i, j, a = tree.intersect_boxes(np.empty((0, 4)))
+    assert i.shape == (0,) and a.shape == (0,)
+    i, j, xy = tree.intersect_edges(np.empty((0, 2, 2)))
+    assert i.shape == (0,) and xy.shape == (0, 2, 2)
+    i, j, a = tree.intersect_faces(np.zeros((3, 2)), np.empty((0, 3), dtype=int), -1)
+    assert i.shape == (0,) and a.shape == (0,)
+
+
+def test_everything_outside_and_nan(delaunay_pair):
+    tree, ref, _, _ = delaunay_pair
+    pts = np.array([[5.0, 5.0], [-3.0, 0.5], [np.nan, 0.5], [0.5, np.nan], [np.inf, 0.5], [0.5, -np.inf]])
+    assert np.array_equal(tree.locate_points(pts), ref.locate_points(pts))
+    boxes = np.array([[2.0, 3.0, 2.0, 3.0], [np.nan, 1.0, 0.0, 1.0], [0.6, 0.4, 0.6, 0.4]])
+    i, j = tree.locate_boxes(boxes)
+    ri, rj = ref.locate_boxes(boxes)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj)
+    edges = np.array([[[2.0, 2.0], [3.0, 3.0]], [[0.5, 0.5], [0.5, 0.5]], [[np.nan, 0.5], [0.6, 0.5]]])
+    i, j, xy = tree.intersect_edges(edges)
+    ri, rj, rxy = ref.intersect_edges(edges)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(xy, rxy, equal_nan=True)
+
+
+def test_single_cell_and_tiny_meshes(pkg):
+    vertices = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    for faces in ([[0, 1, 2]], [[0, 1, 2], [1, 3, 2]], [[0, 1, 3, 2]]):
+        tree = pkg.CellTree2d(vertices, faces, -1)
+        ref = oracle.CellTree2d(vertices, faces, -1)
+        assert_same_tree(tree, ref)
+        pts = np.random.default_rng(0).uniform(-0.5, 1.5, (1000, 2))
+        assert np.array_equal(tree.locate_points(pts), ref.locate_points(pts))
+    with pytest.raises(ValueError):
+        pkg.CellTree2d(vertices, np.empty((0, 3), dtype=int), -1)
+
+
+def geometric_strip(n):
+    """n quads with x-extent halving each time: every split peels off the largest cells => a deep, thin tree."""
+    edges_x = 1.0 / 2.0 ** np.arange(n + 1)
+    vertices = np.concatenate([np.column_stack((edges_x, np.zeros(n + 1))), np.column_stack((edges_x, np.ones(n + 1)))])
+    k = np.arange(n)
+    faces = np.column_stack((k + 1, k, k + n + 1, k + n + 2))
+    return vertices, faces
+
+
+def test_deep_tree_builds_bit_exact_and_traversal_depth_is_checked(pkg):
+    vertices, faces = geometric_strip(60)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    assert_same_tree(tree, ref)
+    pts = np.column_stack((np.random.default_rng(0).uniform(0, 1, 5000) ** 8, np.full(5000, 0.5)))
+    assert np.array_equal(tree.locate_points(pts), ref.locate_points(pts))
+    vertices, faces = geometric_strip(400)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    assert_same_tree(tree, ref)
+    if tree.depth > 64:
+        with pytest.raises(RuntimeError, match="levels"):
+            tree.locate_points(pts)
+
+
+def test_unbucketable_centroid_raises_like_the_reference(pkg):
+    # a zero-width cell at the upper end of the range falls in no bucket: the reference indexes past its
+    # bucket list (IndexError, creation.py:130-131); the oracle and the CUDA build raise IndexError too
+    vertices = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0], [2.0, 0.0], [2.0, 1.0], [2.0, 0.5]])
+    faces = np.array([[0, 1, 2, 3], [1, 4, 5, 2], [4, 5, 6, -1]])
+    with pytest.raises(IndexError):
+        oracle.CellTree2d(vertices, faces, -1, cells_per_leaf=1)
+    with pytest.raises(IndexError):
+        pkg.CellTree2d(vertices, faces, -1, cells_per_leaf=1)
