@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(BLOCK) k_box_area(TreeView t, const double *__
     Poly<4> a;
     box_polygon(load_box(boxes, pi[k]), a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
     double ar = polygon_polygon_clip_area<4, MAXB>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;
@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(BLOCK) k_sat(TreeView t, const int32_t *__rest
     int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (k >= n) return;
     Poly<MAXA> a;
-    load_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
+    gather_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
     flag[k] = (separating_axes<MAXA, MAXB>(a, b) && separating_axes<MAXB, MAXA>(b, a)) ? 1 : 0;
 }
 
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(BLOCK) k_clip_area(TreeView t, const int32_t *
     int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (k >= n) return;
     Poly<MAXA> a;
-    load_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
+    gather_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.vertices, b);
+    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
     double ar = polygon_polygon_clip_area<MAXA, MAXB>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;

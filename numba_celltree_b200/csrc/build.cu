@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(BB) k_pack_nodes(const Node32 *__restrict__ no
         Node32 nd = nodes[i];
         ct_node41 p;
         p.child = nd.child;
-        p.Lmax = nd.Lmax;
-        p.Rmin = nd.Rmin;
+        p.Lmax = nd.child == -1 ? -1.0 : nd.Lmax;  // leaves: the device copy keeps element ids there
+        p.Rmin = nd.child == -1 ? -1.0 : nd.Rmin;
         p.ptr = nd.ptr;
         p.size = nd.size;
         p.dim = (uint8_t)(nd.dim ? 1 : 0);
@@ -655,6 +655,38 @@ __global__ void __launch_bounds__(BB) k_emit_nodes(BuildState st, const int32_t 
     out[final_index[b]] = nd;
 }
 
+// ---- query-side acceleration data derived from the finished tree -----------------------------------------
+// elem_xy: vertex coordinates per element row (see geometry.cuh: load_polygon)
+__global__ void __launch_bounds__(BB) k_elem_coords(const double2 *__restrict__ vertices, const int32_t *__restrict__ elements,
+                                                    int64_t count, double2 *__restrict__ xy) {
+    int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (k >= count) return;
+    int v = elements[k];
+    xy[k] = v >= 0 ? vertices[v] : make_double2(0.0, 0.0);
+}
+
+// leaves carry the first LEAF_INLINE entries of their bb_indices slice in the (unused) plane fields
+__global__ void __launch_bounds__(BB) k_inline_leaf_ids(Node32 *__restrict__ nodes, int64_t n_nodes, const int32_t *__restrict__ bb_indices) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n_nodes) return;
+    Node32 nd = nodes[i];
+    if (nd.child != -1) return;
+    int ids[4];
+    for (int k = 0; k < 4; k++) ids[k] = k < nd.size ? bb_indices[nd.ptr + k] : -1;
+    nodes[i].Lmax = __longlong_as_double(((long long)(unsigned)ids[1] << 32) | (unsigned)ids[0]);
+    nodes[i].Rmin = __longlong_as_double(((long long)(unsigned)ids[3] << 32) | (unsigned)ids[2]);
+}
+
+static int finish_query_data(ct_tree *tree, cudaStream_t s) {
+    const int64_t count = tree->n_elem * tree->M;
+    CT_CUDA(cudaMalloc((void **)&tree->elem_xy, sizeof(double2) * (size_t)(count > 0 ? count : 1)));
+    k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy);
+    CT_LAUNCH_CHECK();
+    k_inline_leaf_ids<<<grid_for(tree->n_nodes, BB), BB, 0, s>>>(tree->nodes, tree->n_nodes, tree->bb_indices);
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
 static int64_t pessimistic_n_nodes(int64_t n_elements) {  // creation.py:216-230
     int64_t n_nodes = n_elements;
     int64_t nodes = (n_elements + 1) / 2;
@@ -985,6 +1017,7 @@ extern "C" int ct_tree_create(const double *vertices, int64_t n_vertex, const in
         }
         CT_CHECK(finish_bounds(tree, s));
         CT_CHECK(build_tree(tree, s));
+        CT_CHECK(finish_query_data(tree, s));
         CT_CUDA(cudaEventRecord(e1, s));
         CT_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -1062,6 +1095,8 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
             tree->depth = d;
         }
         CT_CHECK(finish_bounds(tree, s));
+        CT_CHECK(finish_query_data(tree, s));
+        CT_CUDA(cudaStreamSynchronize(s));
         return CT_OK;
     };
     int status = body();
@@ -1159,5 +1194,6 @@ extern "C" void ct_tree_destroy(ct_tree *tree) {
     cudaFree(tree->bb_coords);
     cudaFree(tree->elements);
     cudaFree(tree->vertices);
+    cudaFree(tree->elem_xy);
     delete tree;
 }

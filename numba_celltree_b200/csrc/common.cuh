@@ -16,6 +16,9 @@ namespace ct {
 // ---- device node: 32 bytes, one L2 sector ---------------------------------------------------------
 // Reference NodeDType is 41 bytes unaligned (constants.py:91-106); the device copy is repacked so that
 // a node is exactly one 32-byte sector and is fetched with two 16-byte loads.
+// A LEAF has no planes (the reference stores Lmax = Rmin = -1.0 there, creation.py:27-29): the device copy
+// uses those 16 bytes for the first four entries of its bb_indices slice, so that the leaf's element ids
+// arrive with the node itself (one dependent load less per query).  ct_tree_download restores the -1.0.
 struct __align__(16) Node32 {
     double Lmax;
     double Rmin;
@@ -35,6 +38,9 @@ struct TreeView {  // passed by value to kernels
     int32_t M;
     int32_t n_elem;
     double bbox[4];
+    // per-element vertex coordinates, (n_elem, M) double2: the polygon of element e is read with one contiguous
+    // access instead of a face row followed by M dependent vertex gathers
+    const double2 *elem_xy;
 };
 
 constexpr int MAX_N_VERTEX = 32;      // constants.py:128
@@ -187,6 +193,7 @@ struct ct_tree {
     double *bb_coords = nullptr;
     int32_t *elements = nullptr;
     double2 *vertices = nullptr;
+    double2 *elem_xy = nullptr;
 
     ct::TreeView view() const {
         ct::TreeView v;
@@ -198,6 +205,7 @@ struct ct_tree {
         v.M = M;
         v.n_elem = (int32_t)n_elem;
         for (int k = 0; k < 4; k++) v.bbox[k] = bbox[k];
+        v.elem_xy = elem_xy;
         return v;
     }
 };

@@ -57,22 +57,43 @@ CT_DEV P2 pget(const Poly<MAXV> &p, int idx) {
 
 // copy_vertices_into (geometry_utils.py:501-510) with polygon_length (:72-79): a face row is scanned for
 // the first -1 from column 3 on; at least 3 vertices are always read.
+// `xy` holds the vertex coordinates per element row, (n, M) double2 (tree: ct_tree.elem_xy, built once from
+// faces + vertices), so the id row (for the length) and the coordinates are two INDEPENDENT loads.
 template <int MAXV>
-CT_DEV void load_polygon(const int32_t *__restrict__ elements, int M, int64_t elem,
-                         const double2 *__restrict__ vertices, Poly<MAXV> &poly) {
-    int idx[MAXV];
+CT_DEV void load_polygon(const int32_t *__restrict__ elements, int M, int64_t elem, const double2 *__restrict__ xy,
+                         Poly<MAXV> &poly) {
     const int32_t *row = elements + elem * (int64_t)M;
+    const double2 *c = xy + elem * (int64_t)M;
+    int n = M < MAXV ? M : MAXV;
     if constexpr (MAXV == 4) {
         if (M == 4) {
             int4 r = __ldg(reinterpret_cast<const int4 *>(row));
-            idx[0] = r.x; idx[1] = r.y; idx[2] = r.z; idx[3] = r.w;
-        } else {
-            idx[0] = __ldg(row); idx[1] = __ldg(row + 1); idx[2] = __ldg(row + 2); idx[3] = -1;
+            if (r.w == -1) n = 3;
         }
-    } else {
+    } else if constexpr (MAXV > 4) {
 #pragma unroll
-        for (int k = 0; k < MAXV; k++) idx[k] = (k < M) ? __ldg(row + k) : -1;
+        for (int k = MAXV - 1; k >= 3; k--)
+            if (k < M && __ldg(row + k) == -1) n = k;
     }
+    poly.n = n;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) {
+        if (k < n) {
+            double2 v = __ldg(c + k);
+            poly.x[k] = v.x;
+            poly.y[k] = v.y;
+        }
+    }
+}
+
+// The same for a polygon given by vertex ids into a vertex array (query faces of ct_locate_faces).
+template <int MAXV>
+CT_DEV void gather_polygon(const int32_t *__restrict__ elements, int M, int64_t elem, const double2 *__restrict__ vertices,
+                           Poly<MAXV> &poly) {
+    int idx[MAXV];
+    const int32_t *row = elements + elem * (int64_t)M;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) idx[k] = (k < M) ? __ldg(row + k) : -1;
     int n = M < MAXV ? M : MAXV;
 #pragma unroll
     for (int k = MAXV - 1; k >= 3; k--)

@@ -35,18 +35,19 @@ __global__ void __launch_bounds__(256) k_morton_keys(const double2 *__restrict__
     idx[i] = (uint32_t)i;
 }
 
-template <int MAXV, bool WEIGHTS>
-__global__ void __launch_bounds__(BLOCK) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
+template <int MAXV, bool WEIGHTS, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                          double tolerance, int64_t *__restrict__ out,
                                                          double *__restrict__ weights, const uint32_t *__restrict__ perm) {
     int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
-    if (perm) i = __ldg(perm + i);
-    double2 pt = __ldg(points + i);
+    // perm / points / results are touched once: streaming accesses keep L1 for the tree
+    if (perm) i = __ldcs(perm + i);
+    double2 pt = __ldcs(points + i);
     P2 p{pt.x, pt.y};
     Poly<MAXV> poly;
     int found = locate_point<MAXV>(t, p, tolerance, poly);
-    out[i] = found;
+    __stcs(out + i, (int64_t)found);
     if constexpr (WEIGHTS) {
         const int M = t.M;
         double *w_out = weights + i * (int64_t)M;
@@ -55,9 +56,9 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points(TreeView t, const doubl
             double u = 0.0, v = 0.0, w = 0.0;
             if (found != -1)
                 triangle_weights(P2{poly.x[0], poly.y[0]}, P2{poly.x[1], poly.y[1]}, P2{poly.x[2], poly.y[2]}, p, u, v, w);
-            w_out[0] = u;
-            w_out[1] = v;
-            w_out[2] = w;
+            __stcs(w_out, u);
+            __stcs(w_out + 1, v);
+            __stcs(w_out + 2, w);
         } else {
             // barycentric_wachspress_weights, algorithms/barycentric_wachspress.py:88-107
             double w[MAXV];
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points(TreeView t, const doubl
             if constexpr (MAXV == 4) {
                 if (M == 4) {
                     double2 *o = reinterpret_cast<double2 *>(w_out);
-                    o[0] = make_double2(w[0], w[1]);
-                    o[1] = make_double2(w[2], w[3]);
+                    __stcs(o, make_double2(w[0], w[1]));
+                    __stcs(o + 1, make_double2(w[2], w[3]));
                     return;
                 }
             }
@@ -84,19 +85,29 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
                                                                  const uint32_t *__restrict__ perm) {
     int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
-    if (perm) i = __ldg(perm + i);
-    double2 pt = __ldg(points + i);
-    out[i] = locate_point_on_edge(t, P2{pt.x, pt.y}, tolerance);
+    if (perm) i = __ldcs(perm + i);
+    double2 pt = __ldcs(points + i);
+    __stcs(out + i, (int64_t)locate_point_on_edge(t, P2{pt.x, pt.y}, tolerance));
 }
 
 template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
                                 const uint32_t *perm, cudaStream_t s) {
     int grid = grid_for(n, BLOCK);
+    // 56 registers (9 blocks of 128 threads per SM) instead of 64: the traversal is latency-bound and one more
+    // resident block per SM is worth the handful of spilled values; tighter caps spill into the hot loop and
+    // lose (measured on C2, ms per 100 M points: 64 regs 12.7, 56 regs 11.9, 48 regs 14.7, 40 regs 17.3).
+    static int minb = -1;
+    if (minb < 0) {
+        const char *e = getenv("CELLTREE_POINTS_MINB");
+        minb = e ? atoi(e) : 9;
+    }
     if (weights)
-        k_locate_points<MAXV, true><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+    else if (MAXV <= 4 && minb == 9)
+        k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
     else
-        k_locate_points<MAXV, false><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
     CT_LAUNCH_CHECK();
     return CT_OK;
 }

@@ -18,6 +18,17 @@ namespace ct {
 
 constexpr int STACK_CAP = 64;
 
+constexpr int LEAF_INLINE = 4;  // element ids stored in a leaf's (unused) plane fields
+
+// k-th element of a leaf: the first LEAF_INLINE ids travel with the node, the rest come from bb_indices
+CT_DEV int leaf_element(const Node32 &node, const int32_t *__restrict__ bb_indices, int k) {
+    if (k < LEAF_INLINE) {
+        long long bits = __double_as_longlong(k < 2 ? node.Lmax : node.Rmin);
+        return (k & 1) ? (int)(bits >> 32) : (int)(bits & 0xffffffffLL);
+    }
+    return __ldg(bb_indices + node.ptr + k);
+}
+
 CT_DEV Node32 load_node(const Node32 *__restrict__ nodes, int idx) {
     // one 32-byte sector, two 16-byte read-only loads
     const double2 *p = reinterpret_cast<const double2 *>(nodes + idx);
@@ -45,9 +56,9 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Poly<MAXV> &p
         Node32 node = load_node(t.nodes, node_index);
         bool pop = false;
         if (node.child == -1) {
-            for (int i = node.ptr; i < node.ptr + node.size; i++) {
-                int bbox_index = __ldg(t.bb_indices + i);
-                load_polygon<MAXV>(t.elements, t.M, bbox_index, t.vertices, poly);
+            for (int k = 0; k < node.size; k++) {
+                int bbox_index = leaf_element(node, t.bb_indices, k);
+                load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, poly);
                 if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
             }
             pop = true;
@@ -90,11 +101,10 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
         Node32 node = load_node(t.nodes, node_index);
         bool pop = false;
         if (node.child == -1) {
-            for (int i = node.ptr; i < node.ptr + node.size; i++) {
-                int bbox_index = __ldg(t.bb_indices + i);
-                int2 e = __ldg(reinterpret_cast<const int2 *>(t.elements) + bbox_index);
-                double2 v0 = __ldg(t.vertices + e.x);
-                double2 v1 = __ldg(t.vertices + e.y);
+            for (int k = 0; k < node.size; k++) {
+                int bbox_index = leaf_element(node, t.bb_indices, k);
+                double2 v0 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
+                double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
                 if (point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return bbox_index;
             }
             pop = true;
@@ -142,8 +152,8 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
         Node32 node = load_node(t.nodes, node_index);
         bool pop = false;
         if (node.child == -1) {
-            for (int i = node.ptr; i < node.ptr + node.size; i++) {
-                int bbox_index = __ldg(t.bb_indices + i);
+            for (int k = 0; k < node.size; k++) {
+                int bbox_index = leaf_element(node, t.bb_indices, k);
                 Box4 leaf_box = load_box(t.bb_coords, bbox_index);
                 if (boxes_intersect(box, leaf_box)) {
                     emit(count, bbox_index);
@@ -184,7 +194,7 @@ CT_DEV bool edge_face_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
     bool intersects = cohen_sutherland_line_box_clip(a, b, box, c, d) != 0;
     if (intersects) {
         Poly<MAXV> polygon;
-        load_polygon<MAXV>(t.elements, t.M, bbox_index, t.vertices, polygon);
+        load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, polygon);
         double tolerance = nb_max(MIN_TOLERANCE, TOLERANCE_FACTOR * nb_max(box.xmax - box.xmin, box.ymax - box.ymin));
         intersects = cyrus_beck_line_polygon_clip<MAXV>(a, b, polygon, tolerance, c, d);
     }
@@ -193,9 +203,8 @@ CT_DEV bool edge_face_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
 
 // compute_edge_edge_intersect, query.py:292-306
 CT_DEV bool edge_edge_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P2 &c, P2 &d) {
-    int2 e = __ldg(reinterpret_cast<const int2 *>(t.elements) + bbox_index);
-    double2 p = __ldg(t.vertices + e.x);
-    double2 q = __ldg(t.vertices + e.y);
+    double2 p = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
+    double2 q = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
     bool intersects = lines_intersect(a, b, P2{p.x, p.y}, P2{q.x, q.y}, c);
     d = c;
     return intersects;
@@ -219,8 +228,8 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
         Node32 node = load_node(t.nodes, node_index);
         bool pop = false;
         if (node.child == -1) {
-            for (int i = node.ptr; i < node.ptr + node.size; i++) {
-                int bbox_index = __ldg(t.bb_indices + i);
+            for (int k = 0; k < node.size; k++) {
+                int bbox_index = leaf_element(node, t.bb_indices, k);
                 P2 c, d;
                 bool intersects;
                 if constexpr (MAXV == 0) intersects = edge_edge_intersect(t, bbox_index, a, b, c, d);
