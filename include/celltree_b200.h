@@ -85,6 +85,11 @@ int64_t ct_launch_count(void);
  * the queries are radix-sorted by before the traversal; 0 = keep the caller's order, -1 = automatic (default;
  * also settable through the environment variable CELLTREE_SORT_BITS). */
 int ct_set_sort_bits(int32_t bits);
+/* Phase timing of ct_locate_points with CT_MEM_DEVICE (CUDA events on the launching stream): when enabled, every
+ * call records events around the Morton ordering and around the traversal kernel; ct_profile_last() waits for the
+ * last call and returns both durations in milliseconds.  bench.py's roofline line uses the traversal figure. */
+int ct_profile_enable(int32_t enable);
+int ct_profile_last(double *order_ms, double *traverse_ms);
 
 /* ---- construction --------------------------------------------------------------------------
  * ct_tree_create replaces the constructor pipeline of CellTree2d.__init__ (celltree.py:74-97) /

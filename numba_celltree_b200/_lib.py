@@ -53,6 +53,8 @@ _SIGNATURES = {
     "ct_set_stream": (ctypes.c_int, [c_void_p]),
     "ct_launch_count": (c_i64, []),
     "ct_set_sort_bits": (ctypes.c_int, [c_i32]),
+    "ct_profile_enable": (ctypes.c_int, [c_i32]),
+    "ct_profile_last": (ctypes.c_int, [ctypes.POINTER(c_f64), ctypes.POINTER(c_f64)]),
     "ct_tree_create": (
         ctypes.c_int,
         [c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_i32, ctypes.POINTER(c_void_p)],

@@ -1,5 +1,6 @@
 // boxes.cu -- ct_locate_boxes / ct_locate_faces: count -> scan -> fill traversal of query boxes, then the
 // per-pair geometry (box or polygon clip area, separating axis test) and order-preserving compaction.
+#include "morton.cuh"
 #include "traverse.cuh"
 
 namespace ct {
@@ -8,9 +9,11 @@ namespace ct {
 template <bool FILL>
 __global__ void __launch_bounds__(BLOCK) k_locate_boxes(TreeView t, const double *__restrict__ boxes, int64_t n,
                                                         int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-                                                        int32_t *__restrict__ out_i, int32_t *__restrict__ out_j) {
+                                                        int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
+                                                        const uint32_t *__restrict__ perm) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (q >= n) return;
+    if (perm) q = __ldg(perm + q);  // execution order only: counts / offsets / pairs are indexed by the query itself
     Box4 box = load_box(boxes, q);
     if constexpr (FILL) {
         int64_t base = offsets[q];
@@ -88,8 +91,10 @@ static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64
     CT_CHECK(offsets.alloc(n + 1, s));
     CT_CUDA(cudaMemsetAsync(counts.p + n, 0, sizeof(int32_t), s));
     int64_t total = 0;
+    MortonOrder order;
+    CT_CHECK(order.build<KEY_BOX>(tree, d_boxes, n, s));
     if (n > 0) {
-        k_locate_boxes<false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr);
+        k_locate_boxes<false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr, order.perm);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -98,7 +103,7 @@ static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64
     r->size = total;
     r->width = 0;
     if (n > 0 && total > 0) {
-        k_locate_boxes<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j);
+        k_locate_boxes<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j, order.perm);
         CT_LAUNCH_CHECK();
     }
     return CT_OK;

@@ -169,6 +169,11 @@ struct DevOut {
 
 
 int check_depth(const ct_tree *tree);
+// phase events of the last ct_locate_points call (lib.cu); nullptr when profiling is off
+struct PhaseEvents {
+    cudaEvent_t start, ordered, done;
+};
+PhaseEvents *phase_events();
 int sort_bits_override();  // -1 = automatic
 // exclusive scan of int32 counts[0..n] (counts[n] must be 0) into int64 offsets[0..n]; *total = offsets[n]
 int scan_counts(const int32_t *counts, int64_t n, int64_t *offsets, int64_t *total, cudaStream_t s);

@@ -1,5 +1,6 @@
 // edges.cu -- ct_intersect_edges: count -> scan -> fill traversal of query segments (Cohen-Sutherland +
 // Cyrus-Beck against faces, segment/segment against a network), then the per-edge stable sort by t.
+#include "morton.cuh"
 #include "traverse.cuh"
 
 namespace ct {
@@ -9,9 +10,10 @@ template <int MAXV, bool FILL>
 __global__ void __launch_bounds__(BLOCK) k_locate_edges(TreeView t, const double *__restrict__ edges, int64_t n,
                                                         int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
                                                         int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
-                                                        double *__restrict__ out_xy) {
+                                                        double *__restrict__ out_xy, const uint32_t *__restrict__ perm) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (q >= n) return;
+    if (perm) q = __ldg(perm + q);  // execution order only
     const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
     double2 a2 = __ldg(e), b2 = __ldg(e + 1);
     P2 a{a2.x, a2.y}, b{b2.x, b2.y};
@@ -77,8 +79,11 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     CT_CHECK(offsets.alloc(n + 1, s));
     CT_CUDA(cudaMemsetAsync(counts.p + n, 0, sizeof(int32_t), s));
     int64_t total = 0;
+    MortonOrder order;
+    CT_CHECK(order.build<KEY_EDGE>(tree, d_edges, n, s));
     if (n > 0) {
-        k_locate_edges<MAXV, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, nullptr, nullptr, nullptr, nullptr);
+        k_locate_edges<MAXV, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, nullptr, nullptr, nullptr, nullptr,
+                                                                        order.perm);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -88,7 +93,8 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     r->size = total;
     r->width = 4;
     if (n > 0 && total > 0) {
-        k_locate_edges<MAXV, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, nullptr, offsets.p, r->i, r->j, r->payload);
+        k_locate_edges<MAXV, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, nullptr, offsets.p, r->i, r->j, r->payload,
+                                                                       order.perm);
         CT_LAUNCH_CHECK();
         k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload);
         CT_LAUNCH_CHECK();

@@ -16,6 +16,23 @@ void set_error(const std::string &msg) { g_error = msg; }
 cudaStream_t current_stream() { return g_stream; }
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
 
+static bool g_profile = false;
+static PhaseEvents g_events;
+static bool g_events_created = false;
+static bool g_events_recorded = false;
+
+PhaseEvents *phase_events() {
+    if (!g_profile) return nullptr;
+    if (!g_events_created) {
+        if (cudaEventCreate(&g_events.start) != cudaSuccess || cudaEventCreate(&g_events.ordered) != cudaSuccess ||
+            cudaEventCreate(&g_events.done) != cudaSuccess)
+            return nullptr;
+        g_events_created = true;
+    }
+    g_events_recorded = true;
+    return &g_events;
+}
+
 static int g_sort_bits = -1;
 int sort_bits_override() {
     static bool env_read = false;
@@ -173,5 +190,25 @@ extern "C" int64_t ct_launch_count(void) { return __atomic_load_n(&g_launches, _
 extern "C" int ct_set_sort_bits(int32_t bits) {
     (void)sort_bits_override();
     g_sort_bits = bits;
+    return CT_OK;
+}
+
+extern "C" int ct_profile_enable(int32_t enable) {
+    g_profile = enable != 0;
+    if (!g_profile) g_events_recorded = false;
+    return CT_OK;
+}
+
+extern "C" int ct_profile_last(double *order_ms, double *traverse_ms) {
+    if (!g_events_created || !g_events_recorded) {
+        set_error("ct_profile_last: no profiled ct_locate_points call");
+        return CT_ERR_VALUE;
+    }
+    CT_CUDA(cudaEventSynchronize(g_events.done));
+    float a = 0.f, b = 0.f;
+    CT_CUDA(cudaEventElapsedTime(&a, g_events.start, g_events.ordered));
+    CT_CUDA(cudaEventElapsedTime(&b, g_events.ordered, g_events.done));
+    if (order_ms) *order_ms = a;
+    if (traverse_ms) *traverse_ms = b;
     return CT_OK;
 }

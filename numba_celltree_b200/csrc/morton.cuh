@@ -1,0 +1,103 @@
+// morton.cuh -- Z-order execution order for a batch of queries (points, boxes, segments).
+//
+// Queries are independent, so the order in which threads pick them up is an execution detail: thread t handles
+// query perm[t] and writes result slot perm[t] (for variable-length results: counts[perm[t]] in the count pass,
+// offsets[perm[t]] in the fill pass -- the OUTPUT order is untouched).  Sorting the queries along a Z-order curve
+// over the tree's bounding box makes the 32 lanes of a warp walk (almost) the same root-to-leaf paths, so node /
+// face / vertex loads collapse to a few sectors per warp and the lower tree levels are served by L1/L2 instead
+// of HBM.  The sort is a CUB radix sort of (key, index) pairs over as many 8-bit passes as the batch size needs.
+#pragma once
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace ct {
+
+enum { KEY_POINT = 0, KEY_BOX = 1, KEY_EDGE = 2 };
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {  // 16 bits -> every other bit of 32
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// representative point of query i: the point itself, the centre of a box (xmin, xmax, ymin, ymax), the midpoint
+// of a segment ((x0, y0), (x1, y1))
+template <int KIND>
+__global__ void __launch_bounds__(256) k_morton_keys(const double *__restrict__ q, int64_t n, double xmin, double ymin, double sx,
+                                                     double sy, int shift, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double x, y;
+    if (KIND == KEY_POINT) {
+        double2 p = __ldg(reinterpret_cast<const double2 *>(q) + i);
+        x = p.x;
+        y = p.y;
+    } else {
+        const double2 *r = reinterpret_cast<const double2 *>(q) + 2 * i;
+        double2 a = __ldg(r), b = __ldg(r + 1);
+        if (KIND == KEY_BOX) {
+            x = 0.5 * (a.x + a.y);
+            y = 0.5 * (b.x + b.y);
+        } else {
+            x = 0.5 * (a.x + b.x);
+            y = 0.5 * (a.y + b.y);
+        }
+    }
+    double fx = (x - xmin) * sx, fy = (y - ymin) * sy;  // [0, 65536) inside the tree's bounding box
+    fx = fx >= 0.0 ? fx : 0.0;                          // also catches NaN
+    fy = fy >= 0.0 ? fy : 0.0;
+    uint32_t ix = fx < 65535.0 ? (uint32_t)fx : 65535u;
+    uint32_t iy = fy < 65535.0 ? (uint32_t)fy : 65535u;
+    keys[i] = (spread16(ix) | (spread16(iy) << 1)) >> shift;
+    idx[i] = (uint32_t)i;
+}
+
+// Number of Morton key bits to sort the queries by; 0 = keep the caller's order.
+// Sorting pays when the tree does not sit in L1/L2 anyway and there are enough queries to amortise the passes.
+inline int sort_bits_for(const ct_tree *tree, int64_t n) {
+    const int forced = sort_bits_override();
+    if (n >= (1LL << 31)) return 0;
+    if (forced >= 0) return forced > 32 ? 32 : forced;
+    const double tree_bytes = 32.0 * (double)tree->n_nodes + (double)tree->n_elem * (4.0 + 20.0 * tree->M);
+    if (n < (1 << 17) || tree_bytes < 8e6) return 0;
+    int bits = 8;  // about one key per query, whole 8-bit radix passes, at most three of them
+    while (bits < 24 && (1LL << bits) < n) bits += 8;
+    return bits;
+}
+
+struct MortonOrder {
+    Scratch<uint32_t> keys_a, keys_b, idx_a, idx_b;
+    Scratch<char> tmp;
+    const uint32_t *perm = nullptr;  // nullptr: run in the caller's order
+
+    template <int KIND>
+    int build(const ct_tree *tree, const double *q, int64_t n, cudaStream_t s) {
+        perm = nullptr;
+        const int bits = sort_bits_for(tree, n);
+        if (bits <= 0 || n <= 0) return CT_OK;
+        CT_CHECK(keys_a.alloc(n, s));
+        CT_CHECK(keys_b.alloc(n, s));
+        CT_CHECK(idx_a.alloc(n, s));
+        CT_CHECK(idx_b.alloc(n, s));
+        double wx = tree->bbox[1] - tree->bbox[0], wy = tree->bbox[3] - tree->bbox[2];
+        double sx = wx > 0 ? 65536.0 / wx : 0.0, sy = wy > 0 ? 65536.0 / wy : 0.0;
+        k_morton_keys<KIND><<<grid_for(n, 256), 256, 0, s>>>(q, n, tree->bbox[0], tree->bbox[2], sx, sy, 32 - bits, keys_a.p, idx_a.p);
+        CT_LAUNCH_CHECK();
+        cub::DoubleBuffer<uint32_t> d_keys(keys_a.p, keys_b.p);
+        cub::DoubleBuffer<uint32_t> d_vals(idx_a.p, idx_b.p);
+        size_t bytes = 0;
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_keys, d_vals, n, 0, bits, s));
+        CT_CHECK(tmp.alloc(bytes, s));
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys, d_vals, n, 0, bits, s));
+        count_launch(1 + (bits + 7) / 8);
+        perm = d_vals.Current();
+        return CT_OK;
+    }
+};
+
+}  // namespace ct

@@ -1,39 +1,9 @@
 // points.cu -- ct_locate_points: Morton ordering of the queries, one-thread-per-point traversal with the
 // point-in-polygon test and fused barycentric weights at the hit.
-#include <cub/device/device_radix_sort.cuh>
-
+#include "morton.cuh"
 #include "traverse.cuh"
 
 namespace ct {
-
-// ---- Morton ordering of the queries -----------------------------------------------------------------------
-// Queries are independent, so the order in which threads pick them up is an execution detail: thread t handles
-// query perm[t] and writes result slot perm[t].  Sorting the queries along a Z-order curve over the tree's
-// bounding box makes the 32 lanes of a warp walk (almost) the same root-to-leaf path, so node / face / vertex
-// loads collapse to a few sectors per warp and the lower tree levels are served by L1/L2 instead of HBM.
-CT_DEV uint32_t spread16(uint32_t v) {  // 16 bits -> every other bit of 32
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
-__global__ void __launch_bounds__(256) k_morton_keys(const double2 *__restrict__ points, int64_t n, double xmin, double ymin,
-                                                     double sx, double sy, int shift, uint32_t *__restrict__ keys,
-                                                     uint32_t *__restrict__ idx) {
-    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    double2 p = __ldg(points + i);
-    double fx = (p.x - xmin) * sx, fy = (p.y - ymin) * sy;  // [0, 65536) inside the tree's bounding box
-    fx = fx >= 0.0 ? fx : 0.0;  // also catches NaN
-    fy = fy >= 0.0 ? fy : 0.0;
-    uint32_t ix = fx < 65535.0 ? (uint32_t)fx : 65535u;
-    uint32_t iy = fy < 65535.0 ? (uint32_t)fy : 65535u;
-    keys[i] = (spread16(ix) | (spread16(iy) << 1)) >> shift;
-    idx[i] = (uint32_t)i;
-}
 
 template <int MAXV, bool WEIGHTS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
@@ -112,60 +82,27 @@ static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n
     return CT_OK;
 }
 
-// Number of Morton key bits to sort the queries by; 0 = keep the caller's order.
-// Sorting pays when the tree is much larger than L2 and there are enough queries to amortise the passes.
-static int sort_bits_for(const ct_tree *tree, int64_t n) {
-    const int forced = sort_bits_override();
-    if (n >= (1LL << 31)) return 0;
-    if (forced >= 0) return forced > 32 ? 32 : forced;
-    const double tree_bytes = 32.0 * (double)tree->n_nodes + (double)tree->n_elem * (4.0 + 4.0 * tree->M) + 16.0 * (double)tree->n_vertex;
-    if (n < (1 << 20) || tree_bytes < 48e6) return 0;
-    int bits = 8;  // about one key per query, whole 8-bit radix passes, at most three of them
-    while (bits < 24 && (1LL << bits) < n) bits += 8;
-    return bits;
-}
-
-// order[] = indices of the points sorted by Morton key (radix sort of (key, index) pairs)
-static int morton_order(const ct_tree *tree, const double2 *pts, int64_t n, int bits, Scratch<uint32_t> &keys_a,
-                        Scratch<uint32_t> &keys_b, Scratch<uint32_t> &idx_a, Scratch<uint32_t> &idx_b, const uint32_t **order,
-                        cudaStream_t s) {
-    CT_CHECK(keys_a.alloc(n, s));
-    CT_CHECK(keys_b.alloc(n, s));
-    CT_CHECK(idx_a.alloc(n, s));
-    CT_CHECK(idx_b.alloc(n, s));
-    double wx = tree->bbox[1] - tree->bbox[0], wy = tree->bbox[3] - tree->bbox[2];
-    double sx = wx > 0 ? 65536.0 / wx : 0.0, sy = wy > 0 ? 65536.0 / wy : 0.0;
-    k_morton_keys<<<grid_for(n, 256), 256, 0, s>>>(pts, n, tree->bbox[0], tree->bbox[2], sx, sy, 32 - bits, keys_a.p, idx_a.p);
-    CT_LAUNCH_CHECK();
-    cub::DoubleBuffer<uint32_t> d_keys(keys_a.p, keys_b.p);
-    cub::DoubleBuffer<uint32_t> d_vals(idx_a.p, idx_b.p);
-    size_t bytes = 0;
-    CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_keys, d_vals, n, 0, bits, s));
-    Scratch<char> tmp;
-    CT_CHECK(tmp.alloc(bytes, s));
-    CT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys, d_vals, n, 0, bits, s));
-    count_launch(1 + (bits + 7) / 8);
-    *order = d_vals.Current();
-    return CT_OK;
-}
-
 static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
-                                cudaStream_t s) {
+                                cudaStream_t s, bool profile = false) {
     if (n == 0) return CT_OK;
     TreeView v = tree->view();
-    Scratch<uint32_t> keys_a, keys_b, idx_a, idx_b;
-    const uint32_t *perm = nullptr;
-    int bits = sort_bits_for(tree, n);
-    if (bits > 0) CT_CHECK(morton_order(tree, pts, n, bits, keys_a, keys_b, idx_a, idx_b, &perm, s));
+    PhaseEvents *ev = profile ? phase_events() : nullptr;
+    if (ev) CT_CUDA(cudaEventRecord(ev->start, s));
+    MortonOrder order;
+    CT_CHECK(order.build<KEY_POINT>(tree, reinterpret_cast<const double *>(pts), n, s));
+    const uint32_t *perm = order.perm;
+    if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
+    int status;
     if (tree->kind == CT_KIND_EDGES) {
         k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, perm);
         CT_LAUNCH_CHECK();
-        return CT_OK;
-    }
-    if (tree->M == 3) return launch_locate_points<3>(v, pts, n, tol, out, weights, perm, s);
-    if (tree->M == 4) return launch_locate_points<4>(v, pts, n, tol, out, weights, perm, s);
-    if (tree->M <= 8) return launch_locate_points<8>(v, pts, n, tol, out, weights, perm, s);
-    return launch_locate_points<32>(v, pts, n, tol, out, weights, perm, s);
+        status = CT_OK;
+    } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, perm, s);
+    else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, perm, s);
+    else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, perm, s);
+    else status = launch_locate_points<32>(v, pts, n, tol, out, weights, perm, s);
+    if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
+    return status;
 }
 
 }  // namespace ct
@@ -186,7 +123,7 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
     CT_CUDA(cudaSetDevice(tree->device));
     cudaStream_t s = current_stream();
     if (mem == CT_MEM_DEVICE)
-        return locate_points_device(tree, reinterpret_cast<const double2 *>(points), n, tolerance, out_index, weights, s);
+        return locate_points_device(tree, reinterpret_cast<const double2 *>(points), n, tolerance, out_index, weights, s, true);
 
     // host buffers: chunked pipeline on two private streams (copy-in / kernel / copy-out overlap)
     const int64_t CHUNK = 1 << 22;
