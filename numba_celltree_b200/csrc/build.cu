@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(BB) k_inline_leaf_ids(Node32 *__restrict__ nod
 
 static int finish_query_data(ct_tree *tree, cudaStream_t s) {
     const int64_t count = tree->n_elem * tree->M;
-    CT_CUDA(cudaMalloc((void **)&tree->elem_xy, sizeof(double2) * (size_t)(count > 0 ? count : 1)));
+    CT_CHECK(dalloc(&tree->elem_xy, (size_t)(count > 0 ? count : 1), s));
     k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy);
     CT_LAUNCH_CHECK();
     k_inline_leaf_ids<<<grid_for(tree->n_nodes, BB), BB, 0, s>>>(tree->nodes, tree->n_nodes, tree->bb_indices);
@@ -874,10 +874,10 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         k_preorder<<<grid_for(hi - lo, BB), BB, 0, s>>>(n_child.p, splits.p, lo, hi, pre_rank.p, final_index.p, level.p, max_level.p);
         CT_LAUNCH_CHECK();
     }
-    CT_CUDA(cudaMalloc((void **)&tree->nodes, sizeof(Node32) * (size_t)node_count));
+    CT_CHECK(dalloc(&tree->nodes, (size_t)node_count, s));
     k_emit_nodes<<<grid_for(node_count, BB), BB, 0, s>>>(st, pre_rank.p, final_index.p, node_count, tree->nodes);
     CT_LAUNCH_CHECK();
-    CT_CUDA(cudaMalloc((void **)&tree->bb_indices, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+    CT_CHECK(dalloc(&tree->bb_indices, (size_t)(n > 0 ? n : 1), s));
     CT_CUDA(cudaMemcpyAsync(tree->bb_indices, idx_cur, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     int32_t h_level = 1;
     CT_CUDA(cudaMemcpyAsync(&h_level, max_level.p, 4, cudaMemcpyDeviceToHost, s));
@@ -924,9 +924,9 @@ static int finish_bounds(ct_tree *tree, cudaStream_t s) {
 static int upload_mesh(ct_tree *tree, const double *vertices, const int64_t *elements, int32_t mem, cudaStream_t s) {
     const int64_t nv = tree->n_vertex, ne = tree->n_elem;
     const int M = tree->M;
-    CT_CUDA(cudaMalloc((void **)&tree->vertices, sizeof(double2) * (size_t)(nv > 0 ? nv : 1)));
-    CT_CUDA(cudaMalloc((void **)&tree->elements, sizeof(int32_t) * (size_t)(ne * M > 0 ? ne * M : 1)));
-    CT_CUDA(cudaMalloc((void **)&tree->bb_coords, sizeof(double) * 4 * (size_t)(ne > 0 ? ne : 1)));
+    CT_CHECK(dalloc(&tree->vertices, (size_t)(nv > 0 ? nv : 1), s));
+    CT_CHECK(dalloc(&tree->elements, (size_t)(ne * M > 0 ? ne * M : 1), s));
+    CT_CHECK(dalloc(&tree->bb_coords, 4 * (size_t)(ne > 0 ? ne : 1), s));
     cudaMemcpyKind kind = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CT_CUDA(cudaMemcpyAsync(tree->vertices, vertices, sizeof(double2) * (size_t)nv, kind, s));
     if (mem == CT_MEM_DEVICE) {
@@ -1062,8 +1062,8 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
         CT_CHECK(upload_mesh(tree, vertices, elements, mem, s));
         cudaMemcpyKind kind_cp = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         CT_CUDA(cudaMemcpyAsync(tree->bb_coords, bb_coords, sizeof(double) * 4 * (size_t)n_elem, kind_cp, s));
-        CT_CUDA(cudaMalloc((void **)&tree->bb_indices, sizeof(int32_t) * (size_t)n_elem));
-        CT_CUDA(cudaMalloc((void **)&tree->nodes, sizeof(Node32) * (size_t)n_nodes));
+        CT_CHECK(dalloc(&tree->bb_indices, (size_t)n_elem, s));
+        CT_CHECK(dalloc(&tree->nodes, (size_t)n_nodes, s));
         {
             Scratch<int64_t> tmp;
             const int64_t *src = bb_indices;
@@ -1189,11 +1189,12 @@ extern "C" int ct_tree_download(const ct_tree *tree, ct_node41 *nodes, int64_t *
 
 extern "C" void ct_tree_destroy(ct_tree *tree) {
     if (!tree) return;
-    cudaFree(tree->nodes);
-    cudaFree(tree->bb_indices);
-    cudaFree(tree->bb_coords);
-    cudaFree(tree->elements);
-    cudaFree(tree->vertices);
-    cudaFree(tree->elem_xy);
+    cudaStream_t s = current_stream();  // the arrays come from the stream-ordered pool
+    dfree(tree->nodes, s);
+    dfree(tree->bb_indices, s);
+    dfree(tree->bb_coords, s);
+    dfree(tree->elements, s);
+    dfree(tree->vertices, s);
+    dfree(tree->elem_xy, s);
     delete tree;
 }
