@@ -128,9 +128,18 @@ class ClockSampler:
         }
 
 
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_rate(tree_data, tolerance, points, target_seconds=12.0):
     """Time the CPU oracle's locate_points on a bounded prefix of `points`; returns (q/s, n, seconds, result)."""
     import oracle
+
+    oracle.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1; the baseline uses every core
 
     probe = min(len(points), 500_000)
     t0 = time.perf_counter()
@@ -153,12 +162,13 @@ def run_reference(args):
     from numba_celltree_b200.synthetic import c2_points, quad_mesh
 
     nx, n_points, name = workload()
-    sample = min(n_points, env_int("CELLTREE_BENCH_REFERENCE_SAMPLE", 4_000_000))
+    sample = min(n_points, env_int("CELLTREE_BENCH_REFERENCE_SAMPLE", 20_000_000))
     vertices, faces = quad_mesh(nx, nx)
     t0 = time.perf_counter()
     tree = oracle.CellTree2d(vertices, faces, -1)
     build_s = time.perf_counter() - t0
     points = c2_points(sample)
+    oracle.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every core
     cores = oracle.num_threads()
     for _ in range(args.warmup):
         oracle.locate_points(points, tree.celltree_data, tree._tolerance)

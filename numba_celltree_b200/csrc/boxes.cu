@@ -106,6 +106,7 @@ static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64
         k_locate_boxes<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j, order.perm);
         CT_LAUNCH_CHECK();
     }
+    trace_point(s, "boxes: count/scan/fill");
     return CT_OK;
 }
 
@@ -181,7 +182,10 @@ extern "C" int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t
             }
             r->payload = area.release();
             r->width = 1;
-            return compact_result(r, flag.p, true, s);
+            trace_point(s, "boxes: clip area");
+            CT_CHECK(compact_result(r, flag.p, true, s));
+            trace_point(s, "boxes: compact");
+            return CT_OK;
         };
         status = stage();
     }

@@ -112,6 +112,9 @@ struct Scratch {
     operator T *() const { return p; }
 };
 
+// CELLTREE_DEBUG=1: synchronise and print the host time since the previous trace point (stderr)
+void trace_point(cudaStream_t s, const char *label);
+
 inline int grid_for(int64_t n, int block) {
     int64_t g = (n + block - 1) / block;
     if (g < 1) g = 1;

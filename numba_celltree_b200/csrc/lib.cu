@@ -3,6 +3,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <ctime>
+
 #include "traverse.cuh"
 
 namespace ct {
@@ -31,6 +33,19 @@ PhaseEvents *phase_events() {
     }
     g_events_recorded = true;
     return &g_events;
+}
+
+void trace_point(cudaStream_t s, const char *label) {
+    static int enabled = -1;
+    static double last = 0.0;
+    if (enabled < 0) enabled = getenv("CELLTREE_DEBUG") ? 1 : 0;
+    if (!enabled) return;
+    cudaStreamSynchronize(s);
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    fprintf(stderr, "[celltree] %-28s +%8.3f ms\n", label, last > 0.0 ? now - last : 0.0);
+    last = now;
 }
 
 static int g_sort_bits = -1;

@@ -141,7 +141,8 @@ def test_faces_and_self_intersection(delaunay_pair):
     np.testing.assert_allclose(a, ra, rtol=RTOL, atol=0)
     # the total overlap equals the area of the triangulated convex hull (size-independent property)
     tri = vertices[faces]
-    hull_area = 0.5 * np.abs(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])).sum()
+    u, w = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    hull_area = 0.5 * np.abs(u[:, 0] * w[:, 1] - u[:, 1] * w[:, 0]).sum()
     assert abs(a.sum() - hull_area) < 1e-9
     # the mesh against itself: sliver pairs at rounding-noise level must match too
     i, j, a = tree.intersect_faces(vertices, faces, -1)
