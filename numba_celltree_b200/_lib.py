@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes
 import pathlib
 
+import os
+
 HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = HERE / "libcelltree_b200.so"
+# CELLTREE_B200_LIB: an experiment build of the same library (build_ext.build_variant), for A/B measurements
+LIB_PATH = pathlib.Path(os.environ.get("CELLTREE_B200_LIB") or HERE / "libcelltree_b200.so")
 
 CT_OK = 0
 CT_ERR_CUDA = 1

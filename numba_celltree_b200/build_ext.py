@@ -37,14 +37,17 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, tag: str = "", defines: tuple = ()) -> pathlib.Path:
+    """Compile and link the library.  `tag` / `defines` make an experiment variant libcelltree_b200_<tag>.so
+    (same sources, extra -D flags) that CELLTREE_B200_LIB can point the binding at."""
+    lib = HERE / f"libcelltree_b200_{tag}.so" if tag else LIB
+    if not tag and not force and not needs_build():
         return LIB
     objs = []
     procs = []
     for src in SOURCES:
-        obj = CSRC / (src.stem + ".o")
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        obj = CSRC / (src.stem + (f"_{tag}" if tag else "") + ".o")
+        cmd = ["nvcc", *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,10 +58,15 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed: {' '.join(cmd)}")
-    link = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+    link = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", str(lib), *map(str, objs)]
     subprocess.run(link, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m numba_celltree_b200.build_ext [--force] [-v] [--variant TAG -DNAME=VALUE ...]
+    if "--variant" in sys.argv:
+        tag = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(force=True, verbose="-v" in sys.argv, tag=tag, defines=tuple(a[2:] for a in sys.argv if a.startswith("-D"))))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

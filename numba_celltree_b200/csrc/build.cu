@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(BB) k_pack_nodes(const Node32 *__restrict__ no
         Node32 nd = nodes[i];
         ct_node41 p;
         p.child = nd.child;
-        p.Lmax = nd.child == -1 ? -1.0 : nd.Lmax;  // leaves: the device copy keeps element ids there
-        p.Rmin = nd.child == -1 ? -1.0 : nd.Rmin;
+        p.Lmax = nd.Lmax;
+        p.Rmin = nd.Rmin;
         p.ptr = nd.ptr;
         p.size = nd.size;
         p.dim = (uint8_t)(nd.dim ? 1 : 0);
@@ -665,16 +665,139 @@ __global__ void __launch_bounds__(BB) k_elem_coords(const double2 *__restrict__ 
     xy[k] = v >= 0 ? vertices[v] : make_double2(0.0, 0.0);
 }
 
-// leaves carry the first LEAF_INLINE entries of their bb_indices slice in the (unused) plane fields
-__global__ void __launch_bounds__(BB) k_inline_leaf_ids(Node32 *__restrict__ nodes, int64_t n_nodes, const int32_t *__restrict__ bb_indices) {
+// ---- treelets (common.cuh): three binary levels per 128-byte line -------------------------------------------------
+// Binary nodes at the seven heap positions of the treelet rooted at `root` (-1: the position does not exist) and
+// the left child of each (-1: leaf, or no such position).
+__device__ __forceinline__ void treelet_positions(const Node32 *__restrict__ nodes, int64_t n_nodes, int root, int node[7],
+                                                  int child[7], int32_t *__restrict__ err) {
+#pragma unroll
+    for (int p = 1; p < 7; p++) node[p] = -1;
+    node[0] = root;
+#pragma unroll
+    for (int p = 0; p < 7; p++) {
+        child[p] = -1;
+        if (node[p] < 0) continue;
+        int c = nodes[node[p]].child;
+        if (c >= 0 && ((int64_t)c + 1 >= n_nodes || c <= node[p])) {  // children always follow their parent
+            *err = 1;
+            c = -1;
+        }
+        child[p] = c;
+        if (p < 3 && c >= 0) {
+            node[2 * p + 1] = c;
+            node[2 * p + 2] = c + 1;
+        }
+    }
+}
+// number of treelets directly below treelet lo + i
+__global__ void __launch_bounds__(BB) k_treelet_count(const Node32 *__restrict__ nodes, int64_t n_nodes, const int32_t *__restrict__ roots,
+                                                     int64_t lo, int64_t n, int32_t *__restrict__ cnt, int32_t *__restrict__ err) {
     int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
-    if (i >= n_nodes) return;
-    Node32 nd = nodes[i];
-    if (nd.child != -1) return;
-    int ids[4];
-    for (int k = 0; k < 4; k++) ids[k] = k < nd.size ? bb_indices[nd.ptr + k] : -1;
-    nodes[i].Lmax = __longlong_as_double(((long long)(unsigned)ids[1] << 32) | (unsigned)ids[0]);
-    nodes[i].Rmin = __longlong_as_double(((long long)(unsigned)ids[3] << 32) | (unsigned)ids[2]);
+    if (i >= n) return;
+    int node[7], child[7];
+    treelet_positions(nodes, n_nodes, roots[lo + i], node, child, err);
+    int c = 0;
+#pragma unroll
+    for (int p = 3; p < 7; p++) c += child[p] >= 0 ? 2 : 0;
+    cnt[i] = c;
+}
+// roots of the next treelet level, in slot order behind those of the treelets before this one
+__global__ void __launch_bounds__(BB) k_treelet_children(const Node32 *__restrict__ nodes, int64_t n_nodes, int32_t *__restrict__ roots,
+                                                        int64_t lo, int64_t n, const int32_t *__restrict__ off, int64_t next_lo,
+                                                        int32_t *__restrict__ child_base, int32_t *__restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n) return;
+    int node[7], child[7];
+    treelet_positions(nodes, n_nodes, roots[lo + i], node, child, err);
+    int64_t base = next_lo + off[i];
+    child_base[lo + i] = (int32_t)base;
+#pragma unroll
+    for (int p = 3; p < 7; p++)
+        if (child[p] >= 0) {
+            roots[base++] = child[p];
+            roots[base++] = child[p] + 1;
+        }
+}
+__global__ void __launch_bounds__(BB) k_treelet_emit(const Node32 *__restrict__ nodes, int64_t n_nodes, const int32_t *__restrict__ bb_indices,
+                                                    const int32_t *__restrict__ roots, const int32_t *__restrict__ child_base, int64_t n,
+                                                    Treelet *__restrict__ out, int32_t *__restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i >= n) return;
+    int node[7], child[7];
+    treelet_positions(nodes, n_nodes, roots[i], node, child, err);
+    Treelet t;
+    uint32_t meta = 0;
+#pragma unroll
+    for (int p = 0; p < 7; p++) {
+        t.plane[p] = make_double2(0.0, 0.0);
+        if (node[p] < 0) continue;
+        const Node32 nd = nodes[node[p]];  // int fields are valid whether or not the leaf ids were inlined already
+        if (child[p] >= 0) {
+            t.plane[p] = make_double2(nd.Lmax, nd.Rmin);
+            if (nd.dim) meta |= 1u << p;
+            if (p >= 3) meta |= 3u << (16 + 2 * (p - 3));
+        } else {
+            int id0 = nd.size > 0 ? bb_indices[nd.ptr] : -1;
+            int id1 = nd.size > 1 ? bb_indices[nd.ptr + 1] : -1;
+            t.plane[p].x = __longlong_as_double(((long long)(unsigned)nd.size << 32) | (unsigned)nd.ptr);
+            t.plane[p].y = __longlong_as_double(((long long)(unsigned)id1 << 32) | (unsigned)id0);
+            meta |= 1u << (8 + p);
+        }
+    }
+    t.child_base = child_base[i];
+    t.meta = meta;
+    t.root_node = roots[i];
+    t.reserved = 0;
+    out[i] = t;
+}
+
+static int build_treelets(ct_tree *tree, cudaStream_t s) {
+    const int64_t n_nodes = tree->n_nodes;
+    Scratch<int32_t> roots, child_base, cnt, off, err;
+    Scratch<char> tmp;
+    CT_CHECK(roots.alloc(n_nodes + 8, s));
+    CT_CHECK(child_base.alloc(n_nodes + 8, s));
+    CT_CHECK(cnt.alloc(n_nodes + 8, s));
+    CT_CHECK(off.alloc(n_nodes + 8, s));
+    CT_CHECK(err.alloc(1, s));
+    CT_CUDA(cudaMemsetAsync(err.p, 0, 4, s));
+    CT_CUDA(cudaMemsetAsync(roots.p, 0, 4, s));  // the first treelet hangs off binary node 0
+    size_t tmp_bytes = 0;
+    CT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, off.p, n_nodes + 1, s));
+    CT_CHECK(tmp.alloc(tmp_bytes, s));
+    int64_t lo = 0, n = 1;
+    while (n > 0) {
+        k_treelet_count<<<grid_for(n, BB), BB, 0, s>>>(tree->nodes, n_nodes, roots.p, lo, n, cnt.p, err.p);
+        CT_LAUNCH_CHECK();
+        size_t bytes = tmp_bytes;
+        CT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, cnt.p, off.p, n, s));
+        count_launch(1);
+        int32_t last[2] = {0, 0};
+        CT_CUDA(cudaMemcpyAsync(&last[0], off.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaMemcpyAsync(&last[1], cnt.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+        const int64_t n_next = (int64_t)last[0] + last[1];
+        if (lo + n + n_next > n_nodes) {  // every binary node heads at most one treelet
+            set_error("malformed tree: the child links do not form a tree");
+            return CT_ERR_VALUE;
+        }
+        k_treelet_children<<<grid_for(n, BB), BB, 0, s>>>(tree->nodes, n_nodes, roots.p, lo, n, off.p, lo + n, child_base.p, err.p);
+        CT_LAUNCH_CHECK();
+        lo += n;
+        n = n_next;
+    }
+    tree->n_treelets = lo;
+    CT_CHECK(dalloc(&tree->treelets, (size_t)lo, s));
+    k_treelet_emit<<<grid_for(lo, BB), BB, 0, s>>>(tree->nodes, n_nodes, tree->bb_indices, roots.p, child_base.p, lo, tree->treelets, err.p);
+    CT_LAUNCH_CHECK();
+    int32_t h_err = 0;
+    CT_CUDA(cudaMemcpyAsync(&h_err, err.p, 4, cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    if (h_err) {
+        set_error("malformed tree: a child index is out of range or does not follow its parent");
+        return CT_ERR_VALUE;
+    }
+    return CT_OK;
 }
 
 static int finish_query_data(ct_tree *tree, cudaStream_t s) {
@@ -682,8 +805,7 @@ static int finish_query_data(ct_tree *tree, cudaStream_t s) {
     CT_CHECK(dalloc(&tree->elem_xy, (size_t)(count > 0 ? count : 1), s));
     k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy);
     CT_LAUNCH_CHECK();
-    k_inline_leaf_ids<<<grid_for(tree->n_nodes, BB), BB, 0, s>>>(tree->nodes, tree->n_nodes, tree->bb_indices);
-    CT_LAUNCH_CHECK();
+    CT_CHECK(build_treelets(tree, s));
     return CT_OK;
 }
 
@@ -1196,5 +1318,6 @@ extern "C" void ct_tree_destroy(ct_tree *tree) {
     dfree(tree->elements, s);
     dfree(tree->vertices, s);
     dfree(tree->elem_xy, s);
+    dfree(tree->treelets, s);
     delete tree;
 }

@@ -13,12 +13,10 @@
 
 namespace ct {
 
-// ---- device node: 32 bytes, one L2 sector ---------------------------------------------------------
-// Reference NodeDType is 41 bytes unaligned (constants.py:91-106); the device copy is repacked so that
-// a node is exactly one 32-byte sector and is fetched with two 16-byte loads.
-// A LEAF has no planes (the reference stores Lmax = Rmin = -1.0 there, creation.py:27-29): the device copy
-// uses those 16 bytes for the first four entries of its bb_indices slice, so that the leaf's element ids
-// arrive with the node itself (one dependent load less per query).  ct_tree_download restores the -1.0.
+// ---- device image of the reference's nodes: 32 bytes -----------------------------------------------------------
+// Reference NodeDType is 41 bytes unaligned (constants.py:91-106); the device copy is repacked to 32 aligned bytes.
+// It is what the build produces and ct_tree_download returns (reference numbering); the queries read the treelets
+// derived from it (below).
 struct __align__(16) Node32 {
     double Lmax;
     double Rmin;
@@ -28,6 +26,26 @@ struct __align__(16) Node32 {
     int32_t dim;    // 0 = x, 1 = y
 };
 static_assert(sizeof(Node32) == 32, "Node32 must be one 32-byte sector");
+
+// ---- treelet: three binary levels in one 128-byte line ------------------------------------------------------
+// The queries walk the tree through TREELETS: the binary node at a level that is a multiple of three, its two
+// children and its four grandchildren (heap positions 0; 1, 2; 3..6) share one 128-byte line, so a descent of
+// three levels costs ONE dependent memory access instead of three, and the up-to-eight treelets below it are
+// stored contiguously (child_base + rank of the slot among the present ones).  A binary node is addressed by the
+// handle (treelet index << 3 | position).  The visiting order of the binary nodes -- what the results depend on --
+// is untouched; Node32 (reference numbering) stays the image that ct_tree_download returns.
+//   plane[p]   inner node: (Lmax, Rmin);  leaf: the bits of {int32 ptr, size, id0, id1} (first two element ids)
+//   child_base index of the first treelet below this one
+//   meta       bit p: dim of position p | bit 8 + p: position p is a leaf | bit 16 + s: child slot s is present
+//              (slot s = child (s & 1) of position 3 + s / 2)
+struct __align__(16) Treelet {
+    double2 plane[7];
+    int32_t child_base;
+    uint32_t meta;
+    int32_t root_node;  // index of the binary node at position 0 (diagnostics)
+    int32_t reserved;
+};
+static_assert(sizeof(Treelet) == 128, "a treelet must be one 128-byte line");
 
 struct TreeView {  // passed by value to kernels
     const Node32 *nodes;
@@ -41,6 +59,7 @@ struct TreeView {  // passed by value to kernels
     // per-element vertex coordinates, (n_elem, M) double2: the polygon of element e is read with one contiguous
     // access instead of a face row followed by M dependent vertex gathers
     const double2 *elem_xy;
+    const Treelet *treelets;
 };
 
 constexpr int MAX_N_VERTEX = 32;      // constants.py:128
@@ -202,6 +221,8 @@ struct ct_tree {
     int32_t *elements = nullptr;
     double2 *vertices = nullptr;
     double2 *elem_xy = nullptr;
+    ct::Treelet *treelets = nullptr;
+    int64_t n_treelets = 0;
 
     ct::TreeView view() const {
         ct::TreeView v;
@@ -214,6 +235,7 @@ struct ct_tree {
         v.n_elem = (int32_t)n_elem;
         for (int k = 0; k < 4; k++) v.bbox[k] = bbox[k];
         v.elem_xy = elem_xy;
+        v.treelets = treelets;
         return v;
     }
 };

@@ -15,11 +15,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const
     if (perm) i = __ldcs(perm + i);
     double2 pt = __ldcs(points + i);
     P2 p{pt.x, pt.y};
-    Poly<MAXV> poly;
-    int found = locate_point<MAXV>(t, p, tolerance, poly);
+    int found = locate_point<MAXV>(t, p, tolerance);
     __stcs(out + i, (int64_t)found);
     if constexpr (WEIGHTS) {
         const int M = t.M;
+        Poly<MAXV> poly;  // the hit face again (its lines are in L1 from the test a moment ago)
+        if (found != -1) load_polygon<MAXV>(t.elements, M, found, t.elem_xy, poly);
         double *w_out = weights + i * (int64_t)M;
         if constexpr (MAXV == 3) {
             // barycentric_triangle_weights, algorithms/barycentric_triangle.py:46-64

@@ -18,122 +18,143 @@ namespace ct {
 
 constexpr int STACK_CAP = 64;
 
-constexpr int LEAF_INLINE = 4;  // element ids stored in a leaf's (unused) plane fields
+constexpr int LEAF_INLINE = 2;  // element ids stored with a leaf position of a treelet
 
-// k-th element of a leaf: the first LEAF_INLINE ids travel with the node, the rest come from bb_indices
-CT_DEV int leaf_element(const Node32 &node, const int32_t *__restrict__ bb_indices, int k) {
-    if (k < LEAF_INLINE) {
-        long long bits = __double_as_longlong(k < 2 ? node.Lmax : node.Rmin);
-        return (k & 1) ? (int)(bits >> 32) : (int)(bits & 0xffffffffLL);
-    }
-    return __ldg(bb_indices + node.ptr + k);
+// ---- the descent, shared by the four traversals ---------------------------------------------------------------
+// Cursor on one binary node.  `plane` is loaded when the cursor moves (one 16-byte load per level); {child_base, meta}
+// only when it enters another treelet, i.e. every third level or after a pop -- both loads are then issued together.
+struct Cursor {
+    uint32_t handle;
+    uint32_t child_base, meta;
+    double2 plane;  // inner: (Lmax, Rmin); leaf: bits of {ptr, size, id0, id1}
+};
+CT_DEV void cursor_load_plane(Cursor &c, const char *__restrict__ base) {
+    // plane of (treelet, position) sits at 128 * treelet + 16 * position = 16 * handle
+    c.plane = __ldg(reinterpret_cast<const double2 *>(base + ((size_t)c.handle << 4)));
 }
-
-CT_DEV Node32 load_node(const Node32 *__restrict__ nodes, int idx) {
-    // one 32-byte sector, two 16-byte read-only loads
-    const double2 *p = reinterpret_cast<const double2 *>(nodes + idx);
-    double2 lr = __ldg(p);
-    int4 m = __ldg(reinterpret_cast<const int4 *>(p + 1));
-    Node32 n;
-    n.Lmax = lr.x;
-    n.Rmin = lr.y;
-    n.child = m.x;
-    n.ptr = m.y;
-    n.size = m.z;
-    n.dim = m.w;
-    return n;
+CT_DEV void cursor_enter(Cursor &c, const char *__restrict__ base, uint32_t handle) {
+    c.handle = handle;
+    const char *line = base + ((size_t)(handle >> 3) << 7);
+    const uint2 tail = __ldg(reinterpret_cast<const uint2 *>(line + 112));
+    cursor_load_plane(c, base);
+    c.child_base = tail.x;
+    c.meta = tail.y;
+}
+CT_DEV bool cursor_is_leaf(const Cursor &c) { return (c.meta >> (8u + (c.handle & 7u))) & 1u; }
+CT_DEV bool cursor_dim(const Cursor &c) { return (c.meta >> (c.handle & 7u)) & 1u; }
+// handles of the two children of the inner node under the cursor
+CT_DEV void cursor_children(const Cursor &c, uint32_t &left, uint32_t &right) {
+    const uint32_t pos = c.handle & 7u;
+    if (pos < 3u) {
+        left = c.handle + pos + 1u;  // same treelet, heap position 2 * pos + 1
+        right = left + 1u;
+    } else {
+        const uint32_t slot = 2u * (pos - 3u);
+        left = (c.child_base + __popc((c.meta >> 16) & ((1u << slot) - 1u))) << 3;
+        right = left + 8u;
+    }
+}
+// move to a child of the node under the cursor
+CT_DEV void cursor_descend(Cursor &c, const char *__restrict__ base, uint32_t child) {
+    if ((c.handle & 7u) < 3u) {
+        c.handle = child;
+        cursor_load_plane(c, base);
+    } else {
+        cursor_enter(c, base, child);
+    }
+}
+CT_DEV int4 cursor_leaf(const Cursor &c) {  // {ptr, size, id0, id1}
+    const long long a = __double_as_longlong(c.plane.x), b = __double_as_longlong(c.plane.y);
+    return make_int4((int)(a & 0xffffffffLL), (int)(a >> 32), (int)(b & 0xffffffffLL), (int)(b >> 32));
+}
+// k-th element of a leaf: the first LEAF_INLINE ids travel with the node, the rest come from bb_indices
+CT_DEV int leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices, int k) {
+    return k == 0 ? leaf.z : (k == 1 ? leaf.w : __ldg(bb_indices + leaf.x + k));
 }
 
 // ---- locate_point, query.py:63-107 ----------------------------------------------------------------------
 // Returns the element index of the first face (in DFS order) that contains the point, -1 if none.
-// On a hit `poly` holds that face's vertices (used by the fused barycentric weights).
+// Two nested loops: the inner one only descends (a handful of registers), the outer one tests the cells of the
+// leaf it arrived at (query.py:72-85) -- so that the register allocation of the descent is not weighed down by
+// the point-in-polygon test.
 template <int MAXV>
-CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Poly<MAXV> &poly) {
-    int stack[STACK_CAP];
+CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
+    uint32_t stack[STACK_CAP];
     int sp = 0;
-    int node_index = 0;
+    const char *base = reinterpret_cast<const char *>(t.treelets);
+    Cursor c;
+    cursor_enter(c, base, 0u);
     while (true) {
-        Node32 node = load_node(t.nodes, node_index);
-        bool pop = false;
-        if (node.child == -1) {
-            for (int k = 0; k < node.size; k++) {
-                int bbox_index = leaf_element(node, t.bb_indices, k);
-                load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, poly);
-                if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
-            }
-            pop = true;
-        } else {
-            double pd = node.dim ? p.y : p.x;
-            bool left = pd <= node.Lmax;
-            bool right = pd >= node.Rmin;
-            int left_child = node.child;
-            int right_child = left_child + 1;
+        while (!cursor_is_leaf(c)) {
+            const double Lmax = c.plane.x, Rmin = c.plane.y;
+            const double pd = cursor_dim(c) ? p.y : p.x;
+            const bool left = pd <= Lmax;
+            const bool right = pd >= Rmin;
+            uint32_t left_handle, right_handle;
+            cursor_children(c, left_handle, right_handle);
             if (left && right) {
                 // nearer-plane heuristic, query.py:93-101: the child pushed LAST is visited first
-                if ((node.Lmax - pd) < (pd - node.Rmin)) {
-                    stack[sp++] = left_child;
-                    node_index = right_child;
-                } else {
-                    stack[sp++] = right_child;
-                    node_index = left_child;
-                }
+                const bool right_first = (Lmax - pd) < (pd - Rmin);
+                stack[sp++] = right_first ? left_handle : right_handle;
+                cursor_descend(c, base, right_first ? right_handle : left_handle);
             } else if (left) {
-                node_index = left_child;
+                cursor_descend(c, base, left_handle);
             } else if (right) {
-                node_index = right_child;
+                cursor_descend(c, base, right_handle);
             } else {
-                pop = true;
+                if (sp == 0) return -1;
+                cursor_enter(c, base, stack[--sp]);
             }
         }
-        if (pop) {
-            if (sp == 0) return -1;
-            node_index = stack[--sp];
+        const int4 leaf = cursor_leaf(c);
+        for (int k = 0; k < leaf.y; k++) {
+            int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            Poly<MAXV> poly;
+            load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, poly);
+            if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
         }
+        if (sp == 0) return -1;
+        cursor_enter(c, base, stack[--sp]);
     }
 }
 
 // ---- locate_point_on_edge, query.py:121-165 ---------------------------------------------------------------
 CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
-    int stack[STACK_CAP];
+    uint32_t stack[STACK_CAP];
     int sp = 0;
-    int node_index = 0;
+    const char *base = reinterpret_cast<const char *>(t.treelets);
+    Cursor c;
+    cursor_enter(c, base, 0u);
     while (true) {
-        Node32 node = load_node(t.nodes, node_index);
-        bool pop = false;
-        if (node.child == -1) {
-            for (int k = 0; k < node.size; k++) {
-                int bbox_index = leaf_element(node, t.bb_indices, k);
-                double2 v0 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
-                double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
-                if (point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return bbox_index;
-            }
-            pop = true;
-        } else {
-            double pd = node.dim ? p.y : p.x;
-            bool left = pd <= node.Lmax;
-            bool right = pd >= node.Rmin;
-            int left_child = node.child;
-            int right_child = left_child + 1;
+        while (!cursor_is_leaf(c)) {
+            const double Lmax = c.plane.x, Rmin = c.plane.y;
+            const double pd = cursor_dim(c) ? p.y : p.x;
+            const bool left = pd <= Lmax;
+            const bool right = pd >= Rmin;
+            uint32_t left_handle, right_handle;
+            cursor_children(c, left_handle, right_handle);
             if (left && right) {
-                if ((node.Lmax - pd) < (pd - node.Rmin)) {
-                    stack[sp++] = left_child;
-                    node_index = right_child;
-                } else {
-                    stack[sp++] = right_child;
-                    node_index = left_child;
-                }
+                const bool right_first = (Lmax - pd) < (pd - Rmin);
+                stack[sp++] = right_first ? left_handle : right_handle;
+                cursor_descend(c, base, right_first ? right_handle : left_handle);
             } else if (left) {
-                node_index = left_child;
+                cursor_descend(c, base, left_handle);
             } else if (right) {
-                node_index = right_child;
+                cursor_descend(c, base, right_handle);
             } else {
-                pop = true;
+                if (sp == 0) return -1;
+                cursor_enter(c, base, stack[--sp]);
             }
         }
-        if (pop) {
-            if (sp == 0) return -1;
-            node_index = stack[--sp];
+        const int4 leaf = cursor_leaf(c);
+        for (int k = 0; k < leaf.y; k++) {
+            int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            double2 v0 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
+            double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
+            if (point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return bbox_index;
         }
+        if (sp == 0) return -1;
+        cursor_enter(c, base, stack[--sp]);
     }
 }
 
@@ -144,45 +165,44 @@ template <typename Emit>
 CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
     Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
     if (!boxes_intersect(box, tree_bbox)) return 0;
-    int stack[STACK_CAP];
+    uint32_t stack[STACK_CAP];
     int sp = 0;
-    int node_index = 0;
     int count = 0;
+    const char *base = reinterpret_cast<const char *>(t.treelets);
+    Cursor c;
+    cursor_enter(c, base, 0u);
     while (true) {
-        Node32 node = load_node(t.nodes, node_index);
-        bool pop = false;
-        if (node.child == -1) {
-            for (int k = 0; k < node.size; k++) {
-                int bbox_index = leaf_element(node, t.bb_indices, k);
-                Box4 leaf_box = load_box(t.bb_coords, bbox_index);
-                if (boxes_intersect(box, leaf_box)) {
-                    emit(count, bbox_index);
-                    count++;
-                }
-            }
-            pop = true;
-        } else {
-            double bmin = node.dim ? box.ymin : box.xmin;
-            double bmax = node.dim ? box.ymax : box.xmax;
-            bool left = bmin <= node.Lmax;
-            bool right = bmax >= node.Rmin;
-            int left_child = node.child;
-            int right_child = left_child + 1;
+        while (!cursor_is_leaf(c)) {
+            const bool dim = cursor_dim(c);
+            const double bmin = dim ? box.ymin : box.xmin;
+            const double bmax = dim ? box.ymax : box.xmax;
+            const bool left = bmin <= c.plane.x;
+            const bool right = bmax >= c.plane.y;
+            uint32_t left_handle, right_handle;
+            cursor_children(c, left_handle, right_handle);
             if (left && right) {
-                stack[sp++] = left_child;
-                node_index = right_child;
+                stack[sp++] = left_handle;
+                cursor_descend(c, base, right_handle);
             } else if (left) {
-                node_index = left_child;
+                cursor_descend(c, base, left_handle);
             } else if (right) {
-                node_index = right_child;
+                cursor_descend(c, base, right_handle);
             } else {
-                pop = true;
+                if (sp == 0) return count;
+                cursor_enter(c, base, stack[--sp]);
             }
         }
-        if (pop) {
-            if (sp == 0) return count;
-            node_index = stack[--sp];
+        const int4 leaf = cursor_leaf(c);
+        for (int k = 0; k < leaf.y; k++) {
+            int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            Box4 leaf_box = load_box(t.bb_coords, bbox_index);
+            if (boxes_intersect(box, leaf_box)) {
+                emit(count, bbox_index);
+                count++;
+            }
         }
+        if (sp == 0) return count;
+        cursor_enter(c, base, stack[--sp]);
     }
 }
 
@@ -220,38 +240,27 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
         if (!cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d)) return 0;
     }
     P2 V = to_vector(a, b);
-    int stack[STACK_CAP];
+    uint32_t stack[STACK_CAP];
     int sp = 0;
-    int node_index = 0;
     int count = 0;
+    const char *base = reinterpret_cast<const char *>(t.treelets);
+    Cursor cur;
+    cursor_enter(cur, base, 0u);
     while (true) {
-        Node32 node = load_node(t.nodes, node_index);
-        bool pop = false;
-        if (node.child == -1) {
-            for (int k = 0; k < node.size; k++) {
-                int bbox_index = leaf_element(node, t.bb_indices, k);
-                P2 c, d;
-                bool intersects;
-                if constexpr (MAXV == 0) intersects = edge_edge_intersect(t, bbox_index, a, b, c, d);
-                else intersects = edge_face_intersect<MAXV>(t, bbox_index, a, b, c, d);
-                if (intersects) {
-                    emit(count, bbox_index, c, d);
-                    count++;
-                }
-            }
-            pop = true;
-        } else {
+        while (!cursor_is_leaf(cur)) {
             // parametric test of the planes Lmax / Rmin along the segment, query.py:407-440
-            double dx = node.dim ? V.y : V.x;
-            double a_d = node.dim ? a.y : a.x;
-            double b_d = node.dim ? b.y : b.x;
+            const bool dim = cursor_dim(cur);
+            const double Lmax = cur.plane.x, Rmin = cur.plane.y;
+            double dx = dim ? V.y : V.x;
+            double a_d = dim ? a.y : a.x;
+            double b_d = dim ? b.y : b.x;
             double dx_left, dx_right;
             if (dx > 0.0) {
-                dx_left = node.Lmax - a_d;
-                dx_right = node.Rmin - b_d;
+                dx_left = Lmax - a_d;
+                dx_right = Rmin - b_d;
             } else {
-                dx_left = node.Lmax - b_d;
-                dx_right = node.Rmin - a_d;
+                dx_left = Lmax - b_d;
+                dx_right = Rmin - a_d;
             }
             bool left = dx_left >= 0.0;
             bool right = dx_right <= 0.0;
@@ -262,23 +271,34 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
                 if (left) left = (1.0 - (dx_left / dx)) >= 0.0;
                 if (right) right = (1.0 - (dx_right / dx)) <= 1.0;
             }
-            int left_child = node.child;
-            int right_child = left_child + 1;
+            uint32_t left_handle, right_handle;
+            cursor_children(cur, left_handle, right_handle);
             if (left && right) {
-                stack[sp++] = left_child;
-                node_index = right_child;
+                stack[sp++] = left_handle;
+                cursor_descend(cur, base, right_handle);
             } else if (left) {
-                node_index = left_child;
+                cursor_descend(cur, base, left_handle);
             } else if (right) {
-                node_index = right_child;
+                cursor_descend(cur, base, right_handle);
             } else {
-                pop = true;
+                if (sp == 0) return count;
+                cursor_enter(cur, base, stack[--sp]);
             }
         }
-        if (pop) {
-            if (sp == 0) return count;
-            node_index = stack[--sp];
+        const int4 leaf = cursor_leaf(cur);
+        for (int k = 0; k < leaf.y; k++) {
+            int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            P2 c, d;
+            bool intersects;
+            if constexpr (MAXV == 0) intersects = edge_edge_intersect(t, bbox_index, a, b, c, d);
+            else intersects = edge_face_intersect<MAXV>(t, bbox_index, a, b, c, d);
+            if (intersects) {
+                emit(count, bbox_index, c, d);
+                count++;
+            }
         }
+        if (sp == 0) return count;
+        cursor_enter(cur, base, stack[--sp]);
     }
 }
 

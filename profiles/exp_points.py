@@ -1,5 +1,5 @@
-"""Experiment: per-kernel timing of locate_points on C2 under different knobs (run under ncu for the launch list)."""
-import os, sys, time
+"""Experiment: locate_points on C2, step / ordering / traversal time (CELLTREE_B200_LIB selects a library variant)."""
+import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from numba_celltree_b200 import CellTree2d, _lib
@@ -7,6 +7,7 @@ from numba_celltree_b200.synthetic import quad_mesh
 nx = int(os.environ.get("NX", 4096)); n = int(os.environ.get("NPTS", 100_000_000))
 v, f = quad_mesh(nx, nx)
 tree = CellTree2d(v, f, -1)
+tree2 = CellTree2d(v, f, -1)
 pts = torch.from_numpy(np.random.default_rng(42).uniform(0, 1, (n, 2))).cuda()
 for _ in range(3): out = tree.locate_points(pts)
 torch.cuda.synchronize()
@@ -14,4 +15,12 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for _ in range(5): out = tree.locate_points(pts)
 e1.record(); torch.cuda.synchronize()
-print("ms/step", e0.elapsed_time(e1) / 5, "Gq/s", n / (e0.elapsed_time(e1) / 5) / 1e6)
+lib = _lib.load()
+lib.ct_profile_enable(1)
+tree.locate_points(pts)
+a, b = ctypes.c_double(), ctypes.c_double()
+lib.ct_profile_last(ctypes.byref(a), ctypes.byref(b))
+lib.ct_profile_enable(0)
+print(os.environ.get("CELLTREE_B200_LIB", "default").split("/")[-1], "ms/step %.3f" % (e0.elapsed_time(e1) / 5),
+      "Gq/s %.3f" % (n / (e0.elapsed_time(e1) / 5) / 1e6), "order %.3f traverse %.3f" % (a.value, b.value),
+      "build %.1f ms" % tree2.build_ms, "checksum", int(out.sum().item()))
