@@ -24,6 +24,7 @@
 #ifndef CELLTREE_B200_H
 #define CELLTREE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -91,6 +92,13 @@ int ct_set_sort_bits(int32_t bits);
 int ct_profile_enable(int32_t enable);
 int ct_profile_last(double *order_ms, double *traverse_ms);
 
+/* Page-locked host memory for results (the reference returns freshly allocated ndarrays, query.py:46-59; a
+ * device-to-host copy into fresh pageable memory runs at a fraction of the PCIe rate).  Blocks are recycled
+ * through a cache inside the library (limit: CELLTREE_PINNED_CACHE_MB, default 8192); ct_host_trim() empties it. */
+int ct_host_alloc(size_t bytes, void **out);
+void ct_host_free(void *block);
+void ct_host_trim(void);
+
 /* ---- construction --------------------------------------------------------------------------
  * ct_tree_create replaces the constructor pipeline of CellTree2d.__init__ (celltree.py:74-97) /
  * EdgeCellTree2d.__init__ (edge_celltree.py:57-83):
@@ -142,11 +150,16 @@ int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t n, int32_t
                     ct_result **out);
 
 /* ct_locate_faces replaces CellTree2d.locate_faces' kernels (celltree.py:212-226): counter_clockwise on
- * the QUERY faces (in place: `faces` is rewritten, as the reference does), build_face_bboxes,
- * locate_boxes, polygons_intersect (separating_axis.py:58-75).  With with_area != 0 it continues with
- * area_of_intersection (sutherland_hodgman.py:151-168) and keeps area > 0 (celltree.py:258-269). */
+ * the QUERY faces, build_face_bboxes, locate_boxes, polygons_intersect (separating_axis.py:58-75).  With
+ * with_area != 0 it continues with area_of_intersection (sutherland_hodgman.py:151-168) and keeps area > 0
+ * (celltree.py:258-269).
+ * fill_value: entries of `faces` equal to it count as padding (cast_faces' rewrite to -1, cast.py:38-39, done
+ * on the device so that the caller's array need not be copied on the host first).
+ * write_back != 0: `faces` is rewritten with the counter-clockwise faces, as locate_faces does to its argument
+ * (celltree.py:212); 0 leaves it untouched (intersect_faces works on a copy, celltree.py:256). */
 int ct_locate_faces(const ct_tree *tree, const double *vertices, int64_t n_vertex, int64_t *faces,
-                    int64_t n_face, int32_t n_max_vert, int32_t with_area, int32_t mem, ct_result **out);
+                    int64_t n_face, int32_t n_max_vert, int64_t fill_value, int32_t write_back,
+                    int32_t with_area, int32_t mem, ct_result **out);
 
 /* ct_intersect_edges replaces query.locate_edge_faces (query.py:542-544, CT_KIND_FACES) /
  * query.locate_edge_edges (query.py:537-539, CT_KIND_EDGES) followed by

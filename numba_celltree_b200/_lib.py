@@ -58,6 +58,9 @@ _SIGNATURES = {
     "ct_set_sort_bits": (ctypes.c_int, [c_i32]),
     "ct_profile_enable": (ctypes.c_int, [c_i32]),
     "ct_profile_last": (ctypes.c_int, [ctypes.POINTER(c_f64), ctypes.POINTER(c_f64)]),
+    "ct_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
+    "ct_host_free": (None, [c_void_p]),
+    "ct_host_trim": (None, []),
     "ct_tree_create": (
         ctypes.c_int,
         [c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_i32, ctypes.POINTER(c_void_p)],
@@ -73,7 +76,7 @@ _SIGNATURES = {
     "ct_locate_boxes": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, ctypes.POINTER(c_void_p)]),
     "ct_locate_faces": (
         ctypes.c_int,
-        [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_void_p)],
+        [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_void_p)],
     ),
     "ct_intersect_edges": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, ctypes.POINTER(c_void_p)]),
     "ct_result_size": (c_i64, [c_void_p]),
@@ -114,3 +117,49 @@ def check(status: int) -> None:
     if status == CT_ERR_UNBUCKETABLE:
         raise IndexError(message)
     raise RuntimeError(f"libcelltree_b200 error {status}: {message}")
+
+
+# ---- result arrays in page-locked host memory -------------------------------------------------------------------
+# A device-to-host copy into a fresh pageable ndarray runs at a fraction of the PCIe rate (driver staging plus a
+# page fault per 4 KiB); results of at least PINNED_MIN_BYTES are therefore NumPy arrays over page-locked blocks
+# that the library recycles (ct_host_alloc / ct_host_free).  CELLTREE_PINNED_RESULTS=0 switches this off.
+PINNED_MIN_BYTES = 1 << 20
+_pinned_results = os.environ.get("CELLTREE_PINNED_RESULTS", "1") != "0"
+
+
+def set_pinned_results(enabled: bool) -> None:
+    global _pinned_results
+    _pinned_results = bool(enabled)
+
+
+class _PinnedBlock:
+    __slots__ = ("address",)
+
+    def __init__(self, address: int):
+        self.address = address
+
+    def __del__(self):
+        try:
+            if _lib is not None and self.address:
+                _lib.ct_host_free(self.address)
+        except Exception:
+            pass
+
+
+def result_array(shape, dtype):
+    """An uninitialised C-contiguous ndarray for a result: page-locked when it is large, plain otherwise."""
+    import numpy as np
+
+    dtype = np.dtype(dtype)
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = dtype.itemsize
+    for x in shape:
+        nbytes *= x
+    if not _pinned_results or nbytes < PINNED_MIN_BYTES:
+        return np.empty(shape, dtype=dtype)
+    address = c_void_p()
+    if load().ct_host_alloc(nbytes, ctypes.byref(address)) != CT_OK or not address.value:
+        return np.empty(shape, dtype=dtype)  # page-locking refused (limits): pageable memory still works
+    buffer = (ctypes.c_char * nbytes).from_address(address.value)
+    buffer._ct_block = _PinnedBlock(address.value)  # the array's base keeps the block alive
+    return np.frombuffer(buffer, dtype=dtype).reshape(shape)

@@ -21,8 +21,7 @@ def cast_vertices(vertices, copy: bool = False):
     return np.ascontiguousarray(vertices)
 
 
-def cast_faces(faces, fill_value: int):
-    faces = _as_array(faces, IntDType, True)
+def check_faces_shape(faces) -> None:
     if faces.ndim != 2:
         raise ValueError("faces must have shape (n_face, n_max_vert)")
     n_max_vert = faces.shape[1]
@@ -31,6 +30,11 @@ def cast_faces(faces, fill_value: int):
             f"faces contains up to {n_max_vert} vertices for a single face. "
             f"A maximum of {MAX_N_VERTEX} vertices per face is supported."
         )
+
+
+def cast_faces(faces, fill_value: int):
+    faces = _as_array(faces, IntDType, True)
+    check_faces_shape(faces)
     if fill_value != FILL_VALUE:
         faces[faces == fill_value] = FILL_VALUE
     return np.ascontiguousarray(faces)

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from numba_celltree_b200 import _lib
-from numba_celltree_b200.cast import cast_bboxes, cast_edges, cast_faces, cast_vertices
+from numba_celltree_b200.cast import cast_bboxes, cast_edges, cast_faces, cast_vertices, check_faces_shape
 from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _is_cuda_tensor, _ptr
 from numba_celltree_b200.constants import FloatArray, IntArray, IntDType, NodeDType
 
@@ -135,12 +135,12 @@ class CellTree2d(CellTree2dBase):
         """Pairs (box index, face index) with a positive area of intersection, and that area."""
         return self._boxes(bbox_coords, with_area=True)
 
-    def _faces(self, vertices, faces, with_area: bool):
+    def _faces(self, vertices, faces, fill_value: int, write_back: bool, with_area: bool):
         handle = ctypes.c_void_p()
         _lib.check(
             _lib.load().ct_locate_faces(
                 self._tree.handle, vertices.ctypes.data, vertices.shape[0], faces.ctypes.data, faces.shape[0],
-                faces.shape[1], int(with_area), _lib.CT_MEM_HOST, ctypes.byref(handle),
+                faces.shape[1], int(fill_value), int(write_back), int(with_area), _lib.CT_MEM_HOST, ctypes.byref(handle),
             )
         )  # fmt: skip
         return self._fetch(handle, payload_shape=())
@@ -157,7 +157,7 @@ class CellTree2d(CellTree2dBase):
             raise ValueError("vertices must have shape (n_points, 2)")
         if faces_c.ndim != 2:
             raise ValueError("faces must have shape (n_face, n_max_vert)")
-        i, j, _ = self._faces(vertices_c, faces_c, with_area=False)
+        i, j, _ = self._faces(vertices_c, faces_c, -1, write_back=True, with_area=False)
         if faces_c is not faces and isinstance(faces, np.ndarray) and faces.shape == faces_c.shape:
             faces[...] = faces_c
         return i, j
@@ -167,8 +167,14 @@ class CellTree2d(CellTree2dBase):
     ) -> Tuple[IntArray, IntArray, FloatArray]:
         """Pairs (face index, tree face index) with a positive area of intersection, and that area."""
         vertices = cast_vertices(vertices)
-        faces = cast_faces(faces, fill_value)
-        return self._faces(vertices, faces, with_area=True)
+        if isinstance(faces, np.ndarray) and faces.dtype == IntDType and faces.flags.c_contiguous:
+            # cast_faces' checks without its copy: the device works on its own copy of the faces and treats
+            # fill_value as padding, so the caller's array is neither modified nor duplicated on the host
+            check_faces_shape(faces)
+        else:
+            faces = cast_faces(faces, fill_value)
+            fill_value = -1
+        return self._faces(vertices, faces, fill_value, write_back=False, with_area=True)
 
     def intersect_edges(self, edge_coords: FloatArray) -> Tuple[IntArray, IntArray, FloatArray]:
         """

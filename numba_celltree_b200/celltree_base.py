@@ -143,10 +143,10 @@ class CellTree2dBase(abc.ABC):
             points = cast_vertices(points)
             n = points.shape[0]
             if out is None:
-                out = np.empty(n, dtype=IntDType)
+                out = _lib.result_array(n, IntDType)
             elif not (isinstance(out, np.ndarray) and out.dtype == IntDType and out.shape == (n,) and out.flags.c_contiguous):
                 raise ValueError("out must be a C-contiguous intp array of shape (n_points,)")
-            weights = np.empty((n, m), dtype=FloatDType) if with_weights else None
+            weights = _lib.result_array((n, m), FloatDType) if with_weights else None
             mem = _lib.CT_MEM_HOST
         _lib.check(lib.ct_locate_points(self._tree.handle, _ptr(points), n, float(tolerance), _ptr(out), _ptr(weights), mem))
         return (out, weights) if with_weights else out
@@ -159,9 +159,9 @@ class CellTree2dBase(abc.ABC):
             total = lib.ct_result_size(handle)
             width = lib.ct_result_payload_width(handle)
             if device is None:
-                i = np.empty(total, dtype=IntDType)
-                j = np.empty(total, dtype=IntDType)
-                payload = np.empty((total,) + tuple(payload_shape), dtype=FloatDType) if width else None
+                i = _lib.result_array(total, IntDType)
+                j = _lib.result_array(total, IntDType)
+                payload = _lib.result_array((total,) + tuple(payload_shape), FloatDType) if width else None
                 mem = _lib.CT_MEM_HOST
             else:
                 import torch

@@ -205,7 +205,8 @@ extern "C" int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t
 }
 
 extern "C" int ct_locate_faces(const ct_tree *tree, const double *vertices, int64_t n_vertex, int64_t *faces, int64_t n_face,
-                               int32_t n_max_vert, int32_t with_area, int32_t mem, ct_result **out) {
+                               int32_t n_max_vert, int64_t fill_value, int32_t write_back, int32_t with_area, int32_t mem,
+                               ct_result **out) {
     if (!tree || !out || n_face < 0 || n_vertex < 0 || (n_face > 0 && (!faces || !vertices))) {
         set_error("ct_locate_faces: null argument");
         return CT_ERR_VALUE;
@@ -234,13 +235,16 @@ extern "C" int ct_locate_faces(const ct_tree *tree, const double *vertices, int6
     ct_result *r = new ct_result();
     auto body = [&]() -> int {
         if (n_face > 0) {
-            CT_CHECK(launch_narrow(d_qf64.p, n_face * qM, qf.p, s));
-            // counter_clockwise on the query faces, in place as the reference does (celltree.py:212)
+            CT_CHECK(launch_narrow(d_qf64.p, n_face * qM, qf.p, s, fill_value));
+            // counter_clockwise on the query faces; written back when the caller's array is to be updated in
+            // place as the reference does (celltree.py:212)
             CT_CHECK(launch_counter_clockwise(qv, qf.p, n_face, qM, s));
-            int64_t *faces_dev = const_cast<int64_t *>(d_qf64.p);
-            CT_CHECK(launch_widen(qf.p, n_face * qM, faces_dev, s));
-            if (mem == CT_MEM_HOST)
-                CT_CUDA(cudaMemcpyAsync(faces, faces_dev, (size_t)n_face * qM * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            if (write_back) {
+                int64_t *faces_dev = const_cast<int64_t *>(d_qf64.p);
+                CT_CHECK(launch_widen(qf.p, n_face * qM, faces_dev, s));
+                if (mem == CT_MEM_HOST)
+                    CT_CUDA(cudaMemcpyAsync(faces, faces_dev, (size_t)n_face * qM * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            }
             CT_CHECK(launch_face_bboxes(qv, qf.p, n_face, qM, qbb.p, s));
         }
         CT_CHECK(locate_boxes_device(tree, qbb.p, n_face, r, s));

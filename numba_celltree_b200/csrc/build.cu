@@ -62,9 +62,12 @@ __global__ void __launch_bounds__(BB) k_widen(const int32_t *__restrict__ in, in
     int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
     if (k < n) out[k] = in[k];
 }
-__global__ void __launch_bounds__(BB) k_narrow(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+__global__ void __launch_bounds__(BB) k_narrow(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out, int64_t fill) {
     int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
-    if (k < n) out[k] = (int32_t)in[k];
+    if (k < n) {
+        const int64_t v = in[k];
+        out[k] = v == fill ? -1 : (int32_t)v;
+    }
 }
 int launch_widen(const int32_t *in, int64_t n, int64_t *out, cudaStream_t s) {
     if (n <= 0) return CT_OK;
@@ -72,9 +75,9 @@ int launch_widen(const int32_t *in, int64_t n, int64_t *out, cudaStream_t s) {
     CT_LAUNCH_CHECK();
     return CT_OK;
 }
-int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s) {
+int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s, int64_t fill) {
     if (n <= 0) return CT_OK;
-    k_narrow<<<grid_for(n, BB), BB, 0, s>>>(in, n, out);
+    k_narrow<<<grid_for(n, BB), BB, 0, s>>>(in, n, out, fill);
     CT_LAUNCH_CHECK();
     return CT_OK;
 }

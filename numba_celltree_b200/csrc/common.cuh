@@ -202,7 +202,8 @@ int scan_counts(const int32_t *counts, int64_t n, int64_t *offsets, int64_t *tot
 // keep the flagged pairs of a result, order preserved
 int compact_result(ct_result *r, const int32_t *flag, bool keep_payload, cudaStream_t s);
 int launch_widen(const int32_t *in, int64_t n, int64_t *out, cudaStream_t s);
-int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s);
+// int64 -> int32; entries equal to `fill` become -1 (cast_faces, cast.py:38-39)
+int launch_narrow(const int64_t *in, int64_t n, int32_t *out, cudaStream_t s, int64_t fill = -1);
 int launch_counter_clockwise(const double2 *vertices, int32_t *faces, int64_t n_face, int M, cudaStream_t s);
 int launch_face_bboxes(const double2 *vertices, const int32_t *faces, int64_t n_face, int M, double *bb, cudaStream_t s);
 }  // namespace ct

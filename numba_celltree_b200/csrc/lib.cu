@@ -4,6 +4,9 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <ctime>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 #include "traverse.cuh"
 
@@ -181,6 +184,87 @@ extern "C" void ct_result_free(ct_result *r) {
     dfree(r->j, s);
     dfree(r->payload, s);
     delete r;
+}
+
+// ---- pinned host memory for results ---------------------------------------------------------------------------
+// Device-to-host copies into fresh pageable memory run at a fraction of the PCIe rate (the driver stages them and
+// every page is faulted in); results therefore go to page-locked blocks that are recycled through a small cache
+// (pinning itself is expensive: it is paid once per size class, not per call).
+namespace {
+struct HostPool {
+    std::mutex lock;
+    std::multimap<size_t, void *> free_blocks;     // by block size
+    std::unordered_map<void *, size_t> block_size;  // every live block
+    size_t cached_bytes = 0;
+    size_t cache_limit = (size_t)8 << 30;
+};
+HostPool g_host_pool;
+// size classes 2^k * {1, 1.25, 1.5, 1.75}: a block serves later requests of a similar size (<= 25 % slack)
+size_t host_size_class(size_t bytes) {
+    size_t base = (size_t)1 << 16;
+    while (base * 2 <= bytes) base *= 2;
+    for (int q = 4; q <= 8; q++) {
+        size_t c = base / 4 * q;
+        if (c >= bytes) return c;
+    }
+    return base * 2;
+}
+}  // namespace
+
+extern "C" int ct_host_alloc(size_t bytes, void **out) {
+    if (!out) {
+        set_error("ct_host_alloc: null argument");
+        return CT_ERR_VALUE;
+    }
+    const size_t size = host_size_class(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> g(g_host_pool.lock);
+        static bool env_read = false;
+        if (!env_read) {
+            env_read = true;
+            if (const char *e = getenv("CELLTREE_PINNED_CACHE_MB")) g_host_pool.cache_limit = (size_t)atoll(e) << 20;
+        }
+        auto it = g_host_pool.free_blocks.find(size);
+        if (it != g_host_pool.free_blocks.end()) {
+            *out = it->second;
+            g_host_pool.cached_bytes -= size;
+            g_host_pool.free_blocks.erase(it);
+            return CT_OK;
+        }
+    }
+    void *p = nullptr;
+    CT_CUDA(cudaHostAlloc(&p, size, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> g(g_host_pool.lock);
+    g_host_pool.block_size[p] = size;
+    *out = p;
+    return CT_OK;
+}
+
+extern "C" void ct_host_free(void *p) {
+    if (!p) return;
+    std::unique_lock<std::mutex> g(g_host_pool.lock);
+    auto it = g_host_pool.block_size.find(p);
+    if (it == g_host_pool.block_size.end()) return;
+    const size_t size = it->second;
+    if (g_host_pool.cached_bytes + size <= g_host_pool.cache_limit) {
+        g_host_pool.free_blocks.emplace(size, p);
+        g_host_pool.cached_bytes += size;
+        return;
+    }
+    g_host_pool.block_size.erase(it);
+    g.unlock();
+    cudaFreeHost(p);
+}
+
+extern "C" void ct_host_trim(void) {
+    std::multimap<size_t, void *> blocks;
+    {
+        std::lock_guard<std::mutex> g(g_host_pool.lock);
+        blocks.swap(g_host_pool.free_blocks);
+        g_host_pool.cached_bytes = 0;
+        for (auto &kv : blocks) g_host_pool.block_size.erase(kv.second);
+    }
+    for (auto &kv : blocks) cudaFreeHost(kv.second);
 }
 
 extern "C" const char *ct_last_error(void) { return g_error.c_str(); }

@@ -151,6 +151,57 @@ def test_faces_and_self_intersection(delaunay_pair):
     assert np.array_equal(a, ra)
 
 
+def test_intersect_faces_leaves_the_callers_faces_alone(delaunay_pair):
+    """intersect_faces works on a copy (celltree.py:256): clockwise query faces with a foreign fill value stay as given."""
+    tree, ref, _, _ = delaunay_pair
+    qv, quads = quad_mesh(60, 60)
+    # mixed mesh: every other quad becomes a triangle padded with -999, all faces clockwise
+    qf = quads[:, ::-1].copy()
+    qf[::2, 3] = -999
+    given = qf.copy()
+    i, j, a = tree.intersect_faces(qv, qf, -999)
+    assert np.array_equal(qf, given)
+    ri, rj, ra = ref.intersect_faces(qv, qf, -999)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra)
+    # a non-contiguous / int32 faces array goes through cast_faces' copy and gives the same pairs
+    i2, j2, a2 = tree.intersect_faces(qv, qf.astype(np.int32), -999)
+    assert np.array_equal(i, i2) and np.array_equal(j, j2) and np.array_equal(a, a2)
+    # locate_faces does rewrite its argument counter-clockwise (celltree.py:212)
+    qf3 = np.where(qf == -999, -1, qf)
+    rf3 = qf3.copy()
+    pi, pj = tree.locate_faces(qv, qf3)
+    rpi, rpj = ref.locate_faces(qv, rf3)
+    assert np.array_equal(pi, rpi) and np.array_equal(pj, rpj)
+    assert np.array_equal(qf3, rf3) and not np.array_equal(qf3, np.where(given == -999, -1, given))
+
+
+def test_results_in_pinned_memory_equal_pageable_results(pkg, delaunay_pair):
+    """Large results live in recycled page-locked blocks; content, dtype and writability are those of plain arrays."""
+    from numba_celltree_b200 import _lib
+
+    tree, _, _, faces = delaunay_pair
+    boxes = c3_boxes(len(faces), 300_000)
+    points = np.random.default_rng(3).uniform(0, 1, (400_000, 2))
+    try:
+        _lib.set_pinned_results(False)
+        plain = tree.intersect_boxes(boxes) + tree.compute_barycentric_weights(points)
+        _lib.set_pinned_results(True)
+        for _ in range(2):  # the second round reuses the blocks released by the first
+            pinned = tree.intersect_boxes(boxes) + tree.compute_barycentric_weights(points)
+            for a, b in zip(plain, pinned):
+                assert a.dtype == b.dtype and a.shape == b.shape and b.flags.writeable and b.flags.c_contiguous
+                assert np.array_equal(a, b)
+            assert pinned[0].nbytes >= _lib.PINNED_MIN_BYTES and not pinned[0].flags.owndata
+            pinned[0][:] = 0  # writable like any result
+            kept = pinned[2].copy()
+            view = pinned[2]
+            del pinned
+            assert np.array_equal(view, kept)  # a surviving result keeps its block
+    finally:
+        _lib.set_pinned_results(True)
+        _lib.load().ct_host_trim()
+
+
 def test_edge_network(pkg):
     from numba_celltree_b200.synthetic import random_network
 
