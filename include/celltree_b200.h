@@ -95,6 +95,10 @@ int ct_profile_last(double *order_ms, double *traverse_ms);
 /* Page-locked host memory for results (the reference returns freshly allocated ndarrays, query.py:46-59; a
  * device-to-host copy into fresh pageable memory runs at a fraction of the PCIe rate).  Blocks are recycled
  * through a cache inside the library (limit: CELLTREE_PINNED_CACHE_MB, default 8192); ct_host_trim() empties it. */
+/* Device memory (trees, scratch, results) is cached inside the library in size classes, so that query calls do not
+ * allocate once their sizes have been seen (limit on cached free bytes: CELLTREE_DEVICE_CACHE_MB, default 65536).
+ * ct_device_trim() returns every cached free block to the driver. */
+void ct_device_trim(void);
 int ct_host_alloc(size_t bytes, void **out);
 void ct_host_free(void *block);
 void ct_host_trim(void);

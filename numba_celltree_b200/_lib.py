@@ -61,6 +61,7 @@ _SIGNATURES = {
     "ct_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
     "ct_host_free": (None, [c_void_p]),
     "ct_host_trim": (None, []),
+    "ct_device_trim": (None, []),
     "ct_tree_create": (
         ctypes.c_int,
         [c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_i32, ctypes.POINTER(c_void_p)],

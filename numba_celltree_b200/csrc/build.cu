@@ -729,28 +729,33 @@ __global__ void __launch_bounds__(BB) k_treelet_emit(const Node32 *__restrict__ 
     int node[7], child[7];
     treelet_positions(nodes, n_nodes, roots[i], node, child, err);
     Treelet t;
-    uint32_t meta = 0;
+    uint32_t meta = 0, child_off = 0;
+    int next_child = 0;
 #pragma unroll
     for (int p = 0; p < 7; p++) {
-        t.plane[p] = make_double2(0.0, 0.0);
+        const int q = p + 1;  // slot
+        t.slot[p] = make_double2(0.0, 0.0);
         if (node[p] < 0) continue;
-        const Node32 nd = nodes[node[p]];  // int fields are valid whether or not the leaf ids were inlined already
+        const Node32 nd = nodes[node[p]];
         if (child[p] >= 0) {
-            t.plane[p] = make_double2(nd.Lmax, nd.Rmin);
-            if (nd.dim) meta |= 1u << p;
-            if (p >= 3) meta |= 3u << (16 + 2 * (p - 3));
+            t.slot[p] = make_double2(nd.Lmax, nd.Rmin);
+            if (nd.dim) meta |= 1u << q;
+            if (p >= 3) {
+                child_off |= (uint32_t)next_child << (4 * (p - 3));
+                next_child += 2;
+            }
         } else {
             int id0 = nd.size > 0 ? bb_indices[nd.ptr] : -1;
             int id1 = nd.size > 1 ? bb_indices[nd.ptr + 1] : -1;
-            t.plane[p].x = __longlong_as_double(((long long)(unsigned)nd.size << 32) | (unsigned)nd.ptr);
-            t.plane[p].y = __longlong_as_double(((long long)(unsigned)id1 << 32) | (unsigned)id0);
-            meta |= 1u << (8 + p);
+            t.slot[p].x = __longlong_as_double(((long long)(unsigned)nd.size << 32) | (unsigned)nd.ptr);
+            t.slot[p].y = __longlong_as_double(((long long)(unsigned)id1 << 32) | (unsigned)id0);
+            meta |= 1u << (8 + q);
         }
     }
     t.child_base = child_base[i];
     t.meta = meta;
+    t.child_off = child_off;
     t.root_node = roots[i];
-    t.reserved = 0;
     out[i] = t;
 }
 
@@ -1015,17 +1020,6 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     return CT_OK;
 }
 
-static int ensure_pool(int device) {
-    static bool done[64] = {false};
-    if (device < 64 && done[device]) return CT_OK;
-    cudaMemPool_t pool;
-    CT_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t threshold = UINT64_MAX;  // keep freed scratch memory cached in the pool
-    CT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    if (device < 64) done[device] = true;
-    return CT_OK;
-}
-
 // bbox_tree + default tolerance from the device bb_coords
 static int finish_bounds(ct_tree *tree, cudaStream_t s) {
     Scratch<unsigned long long> red;
@@ -1117,7 +1111,6 @@ extern "C" int ct_tree_create(const double *vertices, int64_t n_vertex, const in
     CT_CHECK(check_mesh_args(vertices, n_vertex, elements, n_elem, n_max_vert, kind));
     int device = 0;
     CT_CUDA(cudaGetDevice(&device));
-    CT_CHECK(ensure_pool(device));
     cudaStream_t s = current_stream();
     ct_tree *tree = new ct_tree();
     tree->device = device;
@@ -1172,7 +1165,6 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
     CT_CHECK(check_mesh_args(vertices, n_vertex, elements, n_elem, n_max_vert, kind));
     int device = 0;
     CT_CUDA(cudaGetDevice(&device));
-    CT_CHECK(ensure_pool(device));
     cudaStream_t s = current_stream();
     ct_tree *tree = new ct_tree();
     tree->device = device;

@@ -29,21 +29,24 @@ static_assert(sizeof(Node32) == 32, "Node32 must be one 32-byte sector");
 
 // ---- treelet: three binary levels in one 128-byte line ------------------------------------------------------
 // The queries walk the tree through TREELETS: the binary node at a level that is a multiple of three, its two
-// children and its four grandchildren (heap positions 0; 1, 2; 3..6) share one 128-byte line, so a descent of
-// three levels costs ONE dependent memory access instead of three, and the up-to-eight treelets below it are
-// stored contiguously (child_base + rank of the slot among the present ones).  A binary node is addressed by the
-// handle (treelet index << 3 | position).  The visiting order of the binary nodes -- what the results depend on --
-// is untouched; Node32 (reference numbering) stays the image that ct_tree_download returns.
-//   plane[p]   inner node: (Lmax, Rmin);  leaf: the bits of {int32 ptr, size, id0, id1} (first two element ids)
+// children and its four grandchildren share one 128-byte line, so a descent of three levels costs ONE dependent
+// memory access instead of three, and the up-to-eight treelets below it are stored contiguously.  The line holds
+// eight 16-byte slots: slot 0 is the header, slots 1..7 are the binary nodes in heap order (slot q has the children
+// 2q and 2q + 1), so the header and the treelet's root share the first 32-byte sector and siblings share a sector.
+// A binary node is addressed by the handle (treelet index << 3 | slot): its slot sits at byte 16 * handle of the
+// array.  The visiting order of the binary nodes -- what the results depend on -- is untouched; Node32 (reference
+// numbering) stays the image that ct_tree_download returns.
+//   slot q     inner node: (Lmax, Rmin);  leaf: the bits of {int32 ptr, size, id0, id1} (first two element ids)
 //   child_base index of the first treelet below this one
-//   meta       bit p: dim of position p | bit 8 + p: position p is a leaf | bit 16 + s: child slot s is present
-//              (slot s = child (s & 1) of position 3 + s / 2)
+//   meta       bit q: dim of slot q | bit 8 + q: slot q is a leaf
+//   child_off  4 bits per bottom slot q = 4..7 (at bit 4 * (q - 4)): its left child is treelet child_base + that,
+//              its right child the one after
 struct __align__(16) Treelet {
-    double2 plane[7];
     int32_t child_base;
     uint32_t meta;
-    int32_t root_node;  // index of the binary node at position 0 (diagnostics)
-    int32_t reserved;
+    uint32_t child_off;
+    int32_t root_node;  // index of the binary node in slot 1 (diagnostics)
+    double2 slot[7];    // slot[q - 1]
 };
 static_assert(sizeof(Treelet) == 128, "a treelet must be one 128-byte line");
 
@@ -97,16 +100,22 @@ void count_launch(int n = 1);
         CT_CUDA(cudaGetLastError());      \
     } while (0)
 
-// Stream-ordered scratch allocation (cudaMallocAsync pool: no device-wide sync, memory is cached).
+// Device memory comes from a caching pool inside the library (lib.cu): blocks are rounded to a few size classes per
+// octave, freed blocks are kept and handed out again in stream order, so a query call does no cudaMalloc / cudaFree
+// (and none of the driver pool's remapping, which cost 20 ms per call for 2 GB of results) once the sizes have been seen.
+int pool_alloc(void **p, size_t bytes, cudaStream_t s);
+void pool_free(void *p, cudaStream_t s);
+// every block freed on `s` so far is safe for any stream (call after synchronising `s`, e.g. before destroying it)
+void pool_stream_synced(cudaStream_t s);
+
 template <typename T>
 inline int dalloc(T **p, size_t count, cudaStream_t s) {
     *p = nullptr;
     if (count == 0) count = 1;
-    CT_CUDA(cudaMallocAsync((void **)p, count * sizeof(T), s));
-    return CT_OK;
+    return pool_alloc((void **)p, count * sizeof(T), s);
 }
 inline void dfree(void *p, cudaStream_t s) {
-    if (p) cudaFreeAsync(p, s);
+    if (p) pool_free(p, s);
 }
 
 // Owns a stream-ordered allocation for the duration of a call.

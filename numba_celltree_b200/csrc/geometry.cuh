@@ -124,6 +124,15 @@ CT_DEV bool in_bounds(P2 p, P2 a, P2 b) {  // geometry_utils.py:169-192
     return (use_x_bound && ((p.x >= xmin) && (p.x <= xmax))) || (!use_x_bound && ((p.y >= ymin) && (p.y <= ymax)));
 }
 
+// a / b, IEEE-exact.  A zero numerator always takes the software division's slow path (some 70 instructions);
+// on rectilinear meshes every crossing test divides (v1.x - v0.x) * ... = 0 for the vertical edges, so that case
+// is answered directly: (+-0) / (nonzero, non-NaN b) = zero with the sign of a XOR the sign of b.
+CT_DEV double div_exact(double a, double b) {
+    if (a == 0.0 && b != 0.0 && b == b)
+        return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ULL);
+    return a / b;
+}
+
 // geometry_utils.py:195-223 -- crossing-number test with tolerance-based acceptance on the boundary.
 template <int MAXV>
 CT_DEV bool point_in_polygon_or_on_edge(P2 p, const Poly<MAXV> &poly, double tolerance) {
@@ -140,7 +149,7 @@ CT_DEV bool point_in_polygon_or_on_edge(P2 p, const Poly<MAXV> &poly, double tol
         double A = cross_product(U, V);
         P2 W = to_vector(v0, v1);
         if (within_perpendicular_distance(A, W, tolerance) && in_bounds(p, v0, v1)) return true;
-        if (((v0.y > p.y) != (v1.y > p.y)) && (p.x < ((v1.x - v0.x) * (p.y - v0.y) / (v1.y - v0.y) + v0.x))) c = !c;
+        if (((v0.y > p.y) != (v1.y > p.y)) && (p.x < (div_exact((v1.x - v0.x) * (p.y - v0.y), (v1.y - v0.y)) + v0.x))) c = !c;
         v0 = v1;
         U = V;
     }

@@ -124,18 +124,22 @@ int compact_result(ct_result *r, const int32_t *flag, bool keep_payload, cudaStr
             total = last_pos + last_flag;
         }
     }
+    trace_point(s, "  compact: scan");
     int32_t *ni = nullptr, *nj = nullptr;
     double *np_ = nullptr;
     CT_CHECK(dalloc(&ni, total, s));
     CT_CHECK(dalloc(&nj, total, s));
     if (keep_payload) CT_CHECK(dalloc(&np_, total, s));
+    trace_point(s, "  compact: alloc");
     if (n > 0) {
         k_compact<<<grid_for(n, 256), 256, 0, s>>>(flag, pos.p, n, r->i, r->j, keep_payload ? r->payload : nullptr, ni, nj, np_);
         CT_LAUNCH_CHECK();
     }
+    trace_point(s, "  compact: kernel");
     dfree(r->i, s);
     dfree(r->j, s);
     dfree(r->payload, s);
+    trace_point(s, "  compact: free");
     r->i = ni;
     r->j = nj;
     r->payload = np_;
@@ -184,6 +188,127 @@ extern "C" void ct_result_free(ct_result *r) {
     dfree(r->j, s);
     dfree(r->payload, s);
     delete r;
+}
+
+// ---- caching device memory pool (common.cuh: pool_alloc / pool_free) ---------------------------------------------------
+namespace ct {
+namespace {
+cudaStream_t const STREAM_SYNCED = (cudaStream_t)(intptr_t)-1;  // the block may be used on any stream
+struct FreeBlock {
+    void *p;
+    cudaStream_t stream;  // the stream the block was last used and freed on
+    int device;
+};
+struct DevPool {
+    std::mutex lock;
+    std::multimap<size_t, FreeBlock> free_blocks;                // by block size
+    std::unordered_map<void *, std::pair<size_t, int>> live;      // every block: size, device
+    size_t cached_bytes = 0;
+    size_t cache_limit = (size_t)64 << 30;
+    bool env_read = false;
+};
+DevPool g_dev_pool;
+// sizes: 256 B, powers of two up to 1 MiB, then eight classes per octave (<= 12.5 % slack)
+size_t dev_size_class(size_t bytes) {
+    if (bytes <= 256) return 256;
+    size_t base = 256;
+    while (base * 2 <= bytes) base *= 2;
+    if (base == bytes) return base;
+    if (base < ((size_t)1 << 20)) return base * 2;
+    for (int q = 9; q <= 16; q++) {
+        size_t c = base / 8 * q;
+        if (c >= bytes) return c;
+    }
+    return base * 2;
+}
+// cudaFree every cached block of `device` (all devices if < 0); the caller holds the lock
+void dev_pool_release_locked(int device) {
+    for (auto it = g_dev_pool.free_blocks.begin(); it != g_dev_pool.free_blocks.end();) {
+        if (device >= 0 && it->second.device != device) {
+            ++it;
+            continue;
+        }
+        int current = 0;
+        cudaGetDevice(&current);
+        if (current != it->second.device) cudaSetDevice(it->second.device);
+        if (it->second.stream != STREAM_SYNCED) cudaStreamSynchronize(it->second.stream);
+        cudaFree(it->second.p);
+        if (current != it->second.device) cudaSetDevice(current);
+        g_dev_pool.cached_bytes -= it->first;
+        g_dev_pool.live.erase(it->second.p);
+        it = g_dev_pool.free_blocks.erase(it);
+    }
+}
+}  // namespace
+
+int pool_alloc(void **p, size_t bytes, cudaStream_t s) {
+    const size_t size = dev_size_class(bytes);
+    int device = 0;
+    CT_CUDA(cudaGetDevice(&device));
+    {
+        std::unique_lock<std::mutex> g(g_dev_pool.lock);
+        if (!g_dev_pool.env_read) {
+            g_dev_pool.env_read = true;
+            if (const char *e = getenv("CELLTREE_DEVICE_CACHE_MB")) g_dev_pool.cache_limit = (size_t)atoll(e) << 20;
+        }
+        // a cached block of this class that was freed on this stream (reuse is in stream order) or on a stream that
+        // has been synchronised since; blocks other live streams are still using are left to them
+        auto range = g_dev_pool.free_blocks.equal_range(size);
+        for (auto it = range.first; it != range.second; ++it) {
+            if (it->second.device != device) continue;
+            if (it->second.stream == s || it->second.stream == STREAM_SYNCED) {
+                *p = it->second.p;
+                g_dev_pool.free_blocks.erase(it);
+                g_dev_pool.cached_bytes -= size;
+                return CT_OK;
+            }
+        }
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, size);
+    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> g(g_dev_pool.lock);
+            dev_pool_release_locked(device);
+        }
+        CT_CUDA(cudaMalloc(&q, size));
+    }
+    std::lock_guard<std::mutex> g(g_dev_pool.lock);
+    g_dev_pool.live[q] = {size, device};
+    *p = q;
+    return CT_OK;
+}
+
+void pool_free(void *p, cudaStream_t s) {
+    if (!p) return;
+    std::unique_lock<std::mutex> g(g_dev_pool.lock);
+    auto it = g_dev_pool.live.find(p);
+    if (it == g_dev_pool.live.end()) return;
+    const size_t size = it->second.first;
+    const int device = it->second.second;
+    if (g_dev_pool.cached_bytes + size <= g_dev_pool.cache_limit) {
+        g_dev_pool.free_blocks.emplace(size, FreeBlock{p, s, device});
+        g_dev_pool.cached_bytes += size;
+        return;
+    }
+    g_dev_pool.live.erase(it);
+    g.unlock();
+    cudaStreamSynchronize(s);
+    cudaFree(p);
+}
+
+void pool_stream_synced(cudaStream_t s) {
+    std::lock_guard<std::mutex> g(g_dev_pool.lock);
+    for (auto &kv : g_dev_pool.free_blocks)
+        if (kv.second.stream == s) kv.second.stream = STREAM_SYNCED;
+}
+
+}  // namespace ct
+
+extern "C" void ct_device_trim(void) {
+    std::lock_guard<std::mutex> g(ct::g_dev_pool.lock);
+    ct::dev_pool_release_locked(-1);
 }
 
 // ---- pinned host memory for results ---------------------------------------------------------------------------
@@ -280,6 +405,11 @@ extern "C" int ct_set_device(int device) {
 }
 
 extern "C" int ct_set_stream(void *cuda_stream) {
+    if ((cudaStream_t)cuda_stream != g_stream) {
+        // cached blocks freed on the old stream become usable from the new one
+        CT_CUDA(cudaStreamSynchronize(g_stream));
+        pool_stream_synced(g_stream);
+    }
     g_stream = (cudaStream_t)cuda_stream;
     return CT_OK;
 }

@@ -162,6 +162,7 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         dfree(d_out[k], st[k]);
         dfree(d_w[k], st[k]);
         cudaStreamSynchronize(st[k]);
+        pool_stream_synced(st[k]);
         cudaStreamDestroy(st[k]);
     }
     return status;

@@ -16,47 +16,54 @@
 
 namespace ct {
 
+#ifndef CT_LEAF_PREFETCH
+#define CT_LEAF_PREFETCH 0
+#endif
+
 constexpr int STACK_CAP = 64;
 
 constexpr int LEAF_INLINE = 2;  // element ids stored with a leaf position of a treelet
 
 // ---- the descent, shared by the four traversals ---------------------------------------------------------------
-// Cursor on one binary node.  `plane` is loaded when the cursor moves (one 16-byte load per level); {child_base, meta}
-// only when it enters another treelet, i.e. every third level or after a pop -- both loads are then issued together.
+// Cursor on one binary node = (treelet, slot), see common.cuh.  The node's 16-byte slot is loaded when the cursor
+// moves; the treelet header only when it enters another treelet, i.e. every third level or after a pop -- header and
+// root slot then come from the same 32-byte sector.
+constexpr uint32_t ROOT_HANDLE = 1u;  // treelet 0, slot 1
+
 struct Cursor {
     uint32_t handle;
-    uint32_t child_base, meta;
+    uint32_t child_base, meta, child_off;
     double2 plane;  // inner: (Lmax, Rmin); leaf: bits of {ptr, size, id0, id1}
 };
 CT_DEV void cursor_load_plane(Cursor &c, const char *__restrict__ base) {
-    // plane of (treelet, position) sits at 128 * treelet + 16 * position = 16 * handle
     c.plane = __ldg(reinterpret_cast<const double2 *>(base + ((size_t)c.handle << 4)));
 }
 CT_DEV void cursor_enter(Cursor &c, const char *__restrict__ base, uint32_t handle) {
     c.handle = handle;
-    const char *line = base + ((size_t)(handle >> 3) << 7);
-    const uint2 tail = __ldg(reinterpret_cast<const uint2 *>(line + 112));
-    cursor_load_plane(c, base);
-    c.child_base = tail.x;
-    c.meta = tail.y;
+    const char *slot = base + ((size_t)handle << 4);
+    // the header is the first slot of the same (128-byte aligned) line
+    const uint4 header = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(slot) & ~(uintptr_t)127));
+    c.plane = __ldg(reinterpret_cast<const double2 *>(slot));
+    c.child_base = header.x;
+    c.meta = header.y;
+    c.child_off = header.z;
 }
 CT_DEV bool cursor_is_leaf(const Cursor &c) { return (c.meta >> (8u + (c.handle & 7u))) & 1u; }
 CT_DEV bool cursor_dim(const Cursor &c) { return (c.meta >> (c.handle & 7u)) & 1u; }
 // handles of the two children of the inner node under the cursor
 CT_DEV void cursor_children(const Cursor &c, uint32_t &left, uint32_t &right) {
-    const uint32_t pos = c.handle & 7u;
-    if (pos < 3u) {
-        left = c.handle + pos + 1u;  // same treelet, heap position 2 * pos + 1
+    const uint32_t q = c.handle & 7u;
+    if (q < 4u) {
+        left = c.handle + q;  // same treelet, slot 2q
         right = left + 1u;
     } else {
-        const uint32_t slot = 2u * (pos - 3u);
-        left = (c.child_base + __popc((c.meta >> 16) & ((1u << slot) - 1u))) << 3;
+        left = ((c.child_base + ((c.child_off >> (4u * (q - 4u))) & 15u)) << 3) | 1u;
         right = left + 8u;
     }
 }
 // move to a child of the node under the cursor
 CT_DEV void cursor_descend(Cursor &c, const char *__restrict__ base, uint32_t child) {
-    if ((c.handle & 7u) < 3u) {
+    if ((c.handle & 7u) < 4u) {
         c.handle = child;
         cursor_load_plane(c, base);
     } else {
@@ -83,7 +90,7 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
     int sp = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, 0u);
+    cursor_enter(c, base, ROOT_HANDLE);
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;
@@ -107,6 +114,13 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
             }
         }
         const int4 leaf = cursor_leaf(c);
+#if CT_LEAF_PREFETCH
+        if (leaf.y > 1) {  // the second cell's polygon is on its way while the first is tested
+            const char *row = reinterpret_cast<const char *>(t.elem_xy + (int64_t)leaf.w * t.M);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+            if (MAXV > 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 32));
+        }
+#endif
         for (int k = 0; k < leaf.y; k++) {
             int bbox_index = leaf_element(leaf, t.bb_indices, k);
             Poly<MAXV> poly;
@@ -124,7 +138,7 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
     int sp = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, 0u);
+    cursor_enter(c, base, ROOT_HANDLE);
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;
@@ -170,7 +184,7 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, 0u);
+    cursor_enter(c, base, ROOT_HANDLE);
     while (true) {
         while (!cursor_is_leaf(c)) {
             const bool dim = cursor_dim(c);
@@ -245,7 +259,7 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor cur;
-    cursor_enter(cur, base, 0u);
+    cursor_enter(cur, base, ROOT_HANDLE);
     while (true) {
         while (!cursor_is_leaf(cur)) {
             // parametric test of the planes Lmax / Rmin along the segment, query.py:407-440
