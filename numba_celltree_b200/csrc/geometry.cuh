@@ -65,23 +65,36 @@ CT_DEV void load_polygon(const int32_t *__restrict__ elements, int M, int64_t el
     const int32_t *row = elements + elem * (int64_t)M;
     const double2 *c = xy + elem * (int64_t)M;
     int n = M < MAXV ? M : MAXV;
-    if constexpr (MAXV == 4) {
-        if (M == 4) {
-            int4 r = __ldg(reinterpret_cast<const int4 *>(row));
-            if (r.w == -1) n = 3;
+    if constexpr (MAXV <= 4) {
+        // all coordinates are requested before the length is known (the row of xy is complete, padding is (0, 0)):
+        // the id row and the coordinates arrive together instead of one after the other
+        double2 v[MAXV];
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) v[k] = (k < M) ? __ldg(c + k) : make_double2(0.0, 0.0);
+        if constexpr (MAXV == 4) {
+            if (M == 4) {
+                int4 r = __ldg(reinterpret_cast<const int4 *>(row));
+                if (r.w == -1) n = 3;
+            }
         }
-    } else if constexpr (MAXV > 4) {
+        poly.n = n;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            poly.x[k] = v[k].x;
+            poly.y[k] = v[k].y;
+        }
+    } else {
 #pragma unroll
         for (int k = MAXV - 1; k >= 3; k--)
             if (k < M && __ldg(row + k) == -1) n = k;
-    }
-    poly.n = n;
+        poly.n = n;
 #pragma unroll
-    for (int k = 0; k < MAXV; k++) {
-        if (k < n) {
-            double2 v = __ldg(c + k);
-            poly.x[k] = v.x;
-            poly.y[k] = v.y;
+        for (int k = 0; k < MAXV; k++) {
+            if (k < n) {
+                double2 v = __ldg(c + k);
+                poly.x[k] = v.x;
+                poly.y[k] = v.y;
+            }
         }
     }
 }

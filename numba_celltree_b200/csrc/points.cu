@@ -5,49 +5,83 @@
 
 namespace ct {
 
+// Queries per thread.  A thread's queries are gathered together up front: their indices (coalesced reads of `perm`),
+// then their points as asynchronous 16-byte copies into shared memory that are all in flight at once -- the two
+// dependent DRAM round trips (index, then point) are paid once per PER_THREAD queries instead of once per query.
+constexpr int PER_THREAD = 4;
+
+CT_DEV void async_copy_16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+CT_DEV void async_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int MAXV, bool WEIGHTS>
+CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, double *__restrict__ w_out) {
+    const int M = t.M;
+    Poly<MAXV> poly;  // the hit face again (its lines are in L1 from the test a moment ago)
+    if (found != -1) load_polygon<MAXV>(t.elements, M, found, t.elem_xy, poly);
+    if constexpr (MAXV == 3) {
+        // barycentric_triangle_weights, algorithms/barycentric_triangle.py:46-64
+        double u = 0.0, v = 0.0, w = 0.0;
+        if (found != -1)
+            triangle_weights(P2{poly.x[0], poly.y[0]}, P2{poly.x[1], poly.y[1]}, P2{poly.x[2], poly.y[2]}, p, u, v, w);
+        __stcs(w_out, u);
+        __stcs(w_out + 1, v);
+        __stcs(w_out + 2, w);
+    } else {
+        // barycentric_wachspress_weights, algorithms/barycentric_wachspress.py:88-107
+        double w[MAXV];
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) w[k] = 0.0;
+        if (found != -1) wachspress_weights<MAXV>(poly, p, tolerance, w);
+        if constexpr (MAXV == 4) {
+            if (M == 4) {
+                double2 *o = reinterpret_cast<double2 *>(w_out);
+                __stcs(o, make_double2(w[0], w[1]));
+                __stcs(o + 1, make_double2(w[2], w[3]));
+                return;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+            if (k < M) w_out[k] = w[k];
+    }
+}
+
 template <int MAXV, bool WEIGHTS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                          double tolerance, int64_t *__restrict__ out,
                                                          double *__restrict__ weights, const uint32_t *__restrict__ perm) {
-    int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    // perm / points / results are touched once: streaming accesses keep L1 for the tree
-    if (perm) i = __ldcs(perm + i);
-    double2 pt = __ldcs(points + i);
-    P2 p{pt.x, pt.y};
-    int found = locate_point<MAXV>(t, p, tolerance);
-    __stcs(out + i, (int64_t)found);
-    if constexpr (WEIGHTS) {
-        const int M = t.M;
-        Poly<MAXV> poly;  // the hit face again (its lines are in L1 from the test a moment ago)
-        if (found != -1) load_polygon<MAXV>(t.elements, M, found, t.elem_xy, poly);
-        double *w_out = weights + i * (int64_t)M;
-        if constexpr (MAXV == 3) {
-            // barycentric_triangle_weights, algorithms/barycentric_triangle.py:46-64
-            double u = 0.0, v = 0.0, w = 0.0;
-            if (found != -1)
-                triangle_weights(P2{poly.x[0], poly.y[0]}, P2{poly.x[1], poly.y[1]}, P2{poly.x[2], poly.y[2]}, p, u, v, w);
-            __stcs(w_out, u);
-            __stcs(w_out + 1, v);
-            __stcs(w_out + 2, w);
-        } else {
-            // barycentric_wachspress_weights, algorithms/barycentric_wachspress.py:88-107
-            double w[MAXV];
+    __shared__ double2 s_points[PER_THREAD * BLOCK];
+    __shared__ uint32_t s_index[PER_THREAD * BLOCK];
+    const int64_t first = (int64_t)blockIdx.x * (PER_THREAD * BLOCK) + threadIdx.x;
+    // every thread touches only its own shared-memory entries: no barrier is needed
 #pragma unroll
-            for (int k = 0; k < MAXV; k++) w[k] = 0.0;
-            if (found != -1) wachspress_weights<MAXV>(poly, p, tolerance, w);
-            if constexpr (MAXV == 4) {
-                if (M == 4) {
-                    double2 *o = reinterpret_cast<double2 *>(w_out);
-                    __stcs(o, make_double2(w[0], w[1]));
-                    __stcs(o + 1, make_double2(w[2], w[3]));
-                    return;
-                }
+    for (int k = 0; k < PER_THREAD; k++) {
+        const int64_t slot = first + (int64_t)k * BLOCK;
+        if (slot < n) {
+            // perm / points / results are touched once: streaming accesses keep L1 for the tree
+            int64_t i = slot;
+            if (perm) {
+                const uint32_t j = __ldcs(perm + slot);
+                s_index[k * BLOCK + threadIdx.x] = j;
+                i = j;
             }
-#pragma unroll
-            for (int k = 0; k < MAXV; k++)
-                if (k < M) w_out[k] = w[k];
+            async_copy_16(&s_points[k * BLOCK + threadIdx.x], points + i);
         }
+    }
+    async_copy_wait();
+#pragma unroll 1
+    for (int k = 0; k < PER_THREAD; k++) {
+        const int64_t slot = first + (int64_t)k * BLOCK;
+        if (slot >= n) break;
+        const int64_t i = perm ? (int64_t)s_index[k * BLOCK + threadIdx.x] : slot;
+        const double2 pt = s_points[k * BLOCK + threadIdx.x];
+        const P2 p{pt.x, pt.y};
+        const int found = locate_point<MAXV>(t, p, tolerance);
+        __stcs(out + i, (int64_t)found);
+        if constexpr (WEIGHTS) write_weights<MAXV, WEIGHTS>(t, found, p, tolerance, weights + i * (int64_t)t.M);
     }
 }
 
@@ -64,7 +98,7 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
 template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
                                 const uint32_t *perm, cudaStream_t s) {
-    int grid = grid_for(n, BLOCK);
+    int grid = grid_for(n, PER_THREAD * BLOCK);
     // 56 registers (9 blocks of 128 threads per SM) instead of 64: the traversal is latency-bound and one more
     // resident block per SM is worth the handful of spilled values; tighter caps spill into the hot loop and
     // lose (measured on C2, ms per 100 M points: 64 regs 12.7, 56 regs 11.9, 48 regs 14.7, 40 regs 17.3).
@@ -77,6 +111,12 @@ static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n
         k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
     else if (MAXV <= 4 && minb == 9)
         k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+#ifdef CT_EXPERIMENT_MINB
+    else if (MAXV == 4 && minb == 10)
+        k_locate_points<4, false, 10><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+    else if (MAXV == 4 && minb == 12)
+        k_locate_points<4, false, 12><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+#endif
     else
         k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
     CT_LAUNCH_CHECK();
