@@ -74,6 +74,8 @@ struct MortonOrder {
     Scratch<uint32_t> keys_a, keys_b, idx_a, idx_b;
     Scratch<char> tmp;
     const uint32_t *perm = nullptr;  // nullptr: run in the caller's order
+    // after build(): the buffer that holds perm, and the three n-element buffers the sort no longer needs
+    uint32_t *perm_buffer = nullptr, *spare[3] = {nullptr, nullptr, nullptr};
 
     template <int KIND>
     int build(const ct_tree *tree, const double *q, int64_t n, cudaStream_t s) {
@@ -96,8 +98,44 @@ struct MortonOrder {
         CT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys, d_vals, n, 0, bits, s));
         count_launch(1 + (bits + 7) / 8);
         perm = d_vals.Current();
+        perm_buffer = d_vals.Current();
+        spare[0] = d_keys.Current();
+        spare[1] = d_keys.Alternate();
+        spare[2] = d_vals.Alternate();
         return CT_OK;
     }
+
+    // out[perm[t]] = results[t] for results computed in execution order (results = spare[0], int32).
+    // Written directly, these are 8-byte stores all over `out`: every one dirties a 32-byte sector that DRAM must
+    // read, merge and write back.  Instead the (index, result) pairs first go through ONE radix pass on the top
+    // eight bits of the index, which groups them into 256 contiguous windows of `out`; the stores of a window then
+    // meet in L2 and leave it as whole sectors.  perm is consumed.
+    int scatter_results(int64_t n, int64_t *out, cudaStream_t s);
 };
+
+static __global__ void __launch_bounds__(256) k_scatter_results(const uint32_t *__restrict__ index, const uint32_t *__restrict__ value, int64_t n,
+                                                         int64_t *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    out[__ldcs(index + t)] = (int64_t)(int32_t)__ldcs(value + t);
+}
+
+inline int MortonOrder::scatter_results(int64_t n, int64_t *out, cudaStream_t s) {
+    int top = 1;
+    while (top < 32 && ((int64_t)1 << top) < n) top++;
+    const int low = top > 8 ? top - 8 : 0;
+    cub::DoubleBuffer<uint32_t> d_keys(perm_buffer, spare[2]);
+    cub::DoubleBuffer<uint32_t> d_vals(spare[0], spare[1]);
+    size_t bytes = 0;
+    CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_keys, d_vals, n, low, top, s));
+    Scratch<char> tmp2;
+    CT_CHECK(tmp2.alloc(bytes, s));
+    CT_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, bytes, d_keys, d_vals, n, low, top, s));
+    count_launch(2);
+    k_scatter_results<<<grid_for(n, 256), 256, 0, s>>>(d_keys.Current(), d_vals.Current(), n, out);
+    CT_LAUNCH_CHECK();
+    perm = nullptr;
+    return CT_OK;
+}
 
 }  // namespace ct

@@ -52,7 +52,8 @@ CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, 
 template <int MAXV, bool WEIGHTS, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                          double tolerance, int64_t *__restrict__ out,
-                                                         double *__restrict__ weights, const uint32_t *__restrict__ perm) {
+                                                         double *__restrict__ weights, const uint32_t *__restrict__ perm,
+                                                         int32_t *__restrict__ out_in_order) {
     __shared__ double2 s_points[PER_THREAD * BLOCK];
     __shared__ uint32_t s_index[PER_THREAD * BLOCK];
     const int64_t first = (int64_t)blockIdx.x * (PER_THREAD * BLOCK) + threadIdx.x;
@@ -80,24 +81,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const
         const double2 pt = s_points[k * BLOCK + threadIdx.x];
         const P2 p{pt.x, pt.y};
         const int found = locate_point<MAXV>(t, p, tolerance);
-        __stcs(out + i, (int64_t)found);
+        if (out_in_order) out_in_order[slot] = found;  // coalesced; MortonOrder::scatter_results puts it in place
+        else __stcs(out + i, (int64_t)found);
         if constexpr (WEIGHTS) write_weights<MAXV, WEIGHTS>(t, found, p, tolerance, weights + i * (int64_t)t.M);
     }
 }
 
 __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                                  double tolerance, int64_t *__restrict__ out,
-                                                                 const uint32_t *__restrict__ perm) {
-    int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    if (perm) i = __ldcs(perm + i);
+                                                                 const uint32_t *__restrict__ perm, int32_t *__restrict__ out_in_order) {
+    const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (slot >= n) return;
+    const int64_t i = perm ? (int64_t)__ldcs(perm + slot) : slot;
     double2 pt = __ldcs(points + i);
-    __stcs(out + i, (int64_t)locate_point_on_edge(t, P2{pt.x, pt.y}, tolerance));
+    const int found = locate_point_on_edge(t, P2{pt.x, pt.y}, tolerance);
+    if (out_in_order) out_in_order[slot] = found;
+    else __stcs(out + i, (int64_t)found);
 }
 
 template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
-                                const uint32_t *perm, cudaStream_t s) {
+                                const uint32_t *perm, int32_t *in_order, cudaStream_t s) {
     int grid = grid_for(n, PER_THREAD * BLOCK);
     // 56 registers (9 blocks of 128 threads per SM) instead of 64: the traversal is latency-bound and one more
     // resident block per SM is worth the handful of spilled values; tighter caps spill into the hot loop and
@@ -108,17 +112,17 @@ static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n
         minb = e ? atoi(e) : 9;
     }
     if (weights)
-        k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
     else if (MAXV <= 4 && minb == 9)
-        k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
 #ifdef CT_EXPERIMENT_MINB
     else if (MAXV == 4 && minb == 10)
-        k_locate_points<4, false, 10><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<4, false, 10><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
     else if (MAXV == 4 && minb == 12)
-        k_locate_points<4, false, 12><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<4, false, 12><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
 #endif
     else
-        k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm);
+        k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
     CT_LAUNCH_CHECK();
     return CT_OK;
 }
@@ -132,17 +136,24 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
     MortonOrder order;
     CT_CHECK(order.build<KEY_POINT>(tree, reinterpret_cast<const double *>(pts), n, s));
     const uint32_t *perm = order.perm;
+    static int two_phase = -1;
+    if (two_phase < 0) {
+        const char *e = getenv("CELLTREE_SCATTER");
+        two_phase = (e && e[0] == 'd') ? 0 : 1;  // "direct": results are stored straight to out[perm[t]]
+    }
+    int32_t *in_order = (perm && two_phase) ? reinterpret_cast<int32_t *>(order.spare[0]) : nullptr;
     if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
     int status;
     if (tree->kind == CT_KIND_EDGES) {
-        k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, perm);
+        k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, perm, in_order);
         CT_LAUNCH_CHECK();
         status = CT_OK;
-    } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, perm, s);
-    else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, perm, s);
-    else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, perm, s);
-    else status = launch_locate_points<32>(v, pts, n, tol, out, weights, perm, s);
+    } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, perm, in_order, s);
+    else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, perm, in_order, s);
+    else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, perm, in_order, s);
+    else status = launch_locate_points<32>(v, pts, n, tol, out, weights, perm, in_order, s);
     if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
+    if (status == CT_OK && in_order) status = order.scatter_results(n, out, s);
     return status;
 }
 

@@ -6,6 +6,16 @@ from numba_celltree_b200 import CellTree2d, _lib
 from numba_celltree_b200.synthetic import quad_mesh
 nx = int(os.environ.get("NX", 4096)); n = int(os.environ.get("NPTS", 100_000_000))
 v, f = quad_mesh(nx, nx)
+if os.environ.get("L2FETCH"):
+    import glob
+    path = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))[0]
+    rt = ctypes.CDLL(path)
+    torch.cuda.init(); torch.zeros(1).cuda()
+    got = ctypes.c_size_t()
+    rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2FETCH"])))
+    now = ctypes.c_size_t(); rt.cudaDeviceGetLimit(ctypes.byref(now), 5)
+    print("cudaLimitMaxL2FetchGranularity", got.value, "->", now.value, "rc", rc)
 tree = CellTree2d(v, f, -1)
 tree2 = CellTree2d(v, f, -1)
 pts = torch.from_numpy(np.random.default_rng(42).uniform(0, 1, (n, 2))).cuda()
