@@ -30,7 +30,7 @@
 #include <ctime>
 #include <vector>
 
-#include "geometry.cuh"
+#include "traverse.cuh"
 
 namespace ct {
 
@@ -808,12 +808,94 @@ static int build_treelets(ct_tree *tree, cudaStream_t s) {
     return CT_OK;
 }
 
+// ---- entry grid (common.cuh: EntryGrid) ------------------------------------------------------------------------------
+// lo[c]: the smallest double whose grid coordinate reaches column c (bisection over the ordered image; grid_coord is
+// monotone).  lo[0] = -inf; +inf where no double reaches the column.
+__global__ void __launch_bounds__(BB) k_entry_bounds(double vmin, double scale, int bits, double *__restrict__ lo) {
+    const int c = blockIdx.x * BB + threadIdx.x;
+    if (c >= (1 << bits)) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (c == 0) {
+        lo[0] = -inf;
+        return;
+    }
+    const uint32_t target = (uint32_t)c << (16 - bits);
+    unsigned long long a = enc(-inf), b = enc(inf);  // coord(a) < target (it is 0); the answer lies in (a, b]
+    if (grid_coord(inf, vmin, scale) < target) {
+        lo[c] = inf;
+        return;
+    }
+    while (b - a > 1) {
+        const unsigned long long m = a + (b - a) / 2;
+        if (grid_coord(dec(m), vmin, scale) >= target) b = m;
+        else a = m;
+    }
+    lo[c] = dec(b);
+}
+// one thread per cell: descend while the whole cell (lo < v <= hi in both dimensions) takes the same single child
+__global__ void __launch_bounds__(BB) k_entry_table(const Treelet *__restrict__ treelets, const double *__restrict__ lo, int bits,
+                                                   uint32_t *__restrict__ handle) {
+    const int cell = blockIdx.x * BB + threadIdx.x;
+    const int cells = 1 << bits;
+    if (cell >= cells * cells) return;
+    const int cx = cell & (cells - 1), cy = cell >> bits;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double lo_x = lo[cx], lo_y = lo[cells + cy];
+    const double hi_x = cx + 1 < cells ? dec(enc(lo[cx + 1]) - 1) : inf;
+    const double hi_y = cy + 1 < cells ? dec(enc(lo[cells + cy + 1]) - 1) : inf;
+    const char *base = reinterpret_cast<const char *>(treelets);
+    Cursor c;
+    cursor_enter(c, base, ROOT_HANDLE);
+    while (!cursor_is_leaf(c)) {
+        const bool dim = cursor_dim(c);
+        const double cell_lo = dim ? lo_y : lo_x, cell_hi = dim ? hi_y : hi_x;
+        const double Lmax = c.plane.x, Rmin = c.plane.y;
+        // every v <= hi has "v <= Lmax" and not "v >= Rmin"; every v > lo has "v >= Rmin" and not "v <= Lmax"
+        const bool left_only = (cell_hi <= Lmax) && (cell_hi < Rmin);
+        const bool right_only = (cell_lo >= Rmin) && (cell_lo >= Lmax);
+        if (!(left_only || right_only)) break;
+        uint32_t left, right;
+        cursor_children(c, left, right);
+        cursor_descend(c, base, left_only ? left : right);
+    }
+    handle[cell] = c.handle;
+}
+
+static int build_entry_grid(ct_tree *tree, cudaStream_t s) {
+    const double wx = tree->bbox[1] - tree->bbox[0], wy = tree->bbox[3] - tree->bbox[2];
+    tree->grid_sx = wx > 0 ? 65536.0 / wx : 0.0;
+    tree->grid_sy = wy > 0 ? 65536.0 / wy : 0.0;
+    const bool usable = tree->grid_sx > 0.0 && tree->grid_sy > 0.0 && tree->grid_sx < FLOAT_MAX && tree->grid_sy < FLOAT_MAX;
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("CELLTREE_ENTRY_BITS");  // experiments: 0 switches the grid off
+        forced = e ? atoi(e) : -1;
+    }
+    // about 64 elements per cell
+    int bits = 0;
+    while (bits < 10 && ((int64_t)64 << (2 * (bits + 1))) <= tree->n_elem) bits++;
+    if (forced >= 0) bits = forced > 10 ? 10 : forced;
+    if (!usable || bits < 2) return CT_OK;
+    const int cells = 1 << bits;
+    CT_CHECK(dalloc(&tree->entry_lo, (size_t)2 * cells, s));
+    CT_CHECK(dalloc(&tree->entry_handle, (size_t)cells * cells, s));
+    k_entry_bounds<<<grid_for(cells, BB), BB, 0, s>>>(tree->bbox[0], tree->grid_sx, bits, tree->entry_lo);
+    CT_LAUNCH_CHECK();
+    k_entry_bounds<<<grid_for(cells, BB), BB, 0, s>>>(tree->bbox[2], tree->grid_sy, bits, tree->entry_lo + cells);
+    CT_LAUNCH_CHECK();
+    k_entry_table<<<grid_for((int64_t)cells * cells, BB), BB, 0, s>>>(tree->treelets, tree->entry_lo, bits, tree->entry_handle);
+    CT_LAUNCH_CHECK();
+    tree->entry_bits = bits;
+    return CT_OK;
+}
+
 static int finish_query_data(ct_tree *tree, cudaStream_t s) {
     const int64_t count = tree->n_elem * tree->M;
     CT_CHECK(dalloc(&tree->elem_xy, (size_t)(count > 0 ? count : 1), s));
     k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy);
     CT_LAUNCH_CHECK();
     CT_CHECK(build_treelets(tree, s));
+    CT_CHECK(build_entry_grid(tree, s));
     return CT_OK;
 }
 
@@ -1314,5 +1396,7 @@ extern "C" void ct_tree_destroy(ct_tree *tree) {
     dfree(tree->vertices, s);
     dfree(tree->elem_xy, s);
     dfree(tree->treelets, s);
+    dfree(tree->entry_handle, s);
+    dfree(tree->entry_lo, s);
     delete tree;
 }

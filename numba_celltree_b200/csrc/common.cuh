@@ -50,6 +50,27 @@ struct __align__(16) Treelet {
 };
 static_assert(sizeof(Treelet) == 128, "a treelet must be one 128-byte line");
 
+// ---- entry grid of the point queries -----------------------------------------------------------------------------
+// A uniform grid over the tree's bounding box whose cell (cx, cy) holds the handle of the deepest node that EVERY point
+// of the cell reaches by single-child decisions -- at each ancestor exactly one of "x <= Lmax" / "x >= Rmin" holds for the
+// whole cell -- so a point query starts there instead of at the root with the reference's visiting order intact (no
+// ancestor could have pushed a sibling).  A cell is the set of doubles v with lo[c] < v <= hi[c] whose grid_coord() is c;
+// a point that sits exactly on lo[c] (it may lie on a split plane and then goes both ways) starts at the root, and so
+// does everything grid_coord() clamps from outside the box or NaN.
+struct EntryGrid {
+    const uint32_t *handle;  // (cells, cells), row = cy; nullptr: always start at the root
+    const double *lo;        // lo_x[cells] then lo_y[cells]: the smallest double of every column / row
+    int32_t bits;            // cells = 1 << bits per side
+    double xmin, ymin, sx, sy;
+};
+
+// 16-bit grid coordinate of a value over [vmin, vmin + 65536 / scale): monotone in v; below the box and NaN -> 0
+__device__ __forceinline__ uint32_t grid_coord(double v, double vmin, double scale) {
+    double f = (v - vmin) * scale;
+    f = f >= 0.0 ? f : 0.0;
+    return f < 65535.0 ? (uint32_t)f : 65535u;
+}
+
 struct TreeView {  // passed by value to kernels
     const Node32 *nodes;
     const int32_t *bb_indices;
@@ -63,6 +84,7 @@ struct TreeView {  // passed by value to kernels
     // access instead of a face row followed by M dependent vertex gathers
     const double2 *elem_xy;
     const Treelet *treelets;
+    EntryGrid entry;
 };
 
 constexpr int MAX_N_VERTEX = 32;      // constants.py:128
@@ -233,6 +255,10 @@ struct ct_tree {
     double2 *elem_xy = nullptr;
     ct::Treelet *treelets = nullptr;
     int64_t n_treelets = 0;
+    uint32_t *entry_handle = nullptr;
+    double *entry_lo = nullptr;
+    int32_t entry_bits = 0;
+    double grid_sx = 0.0, grid_sy = 0.0;  // 65536 / bbox width, height (0 when the box is degenerate)
 
     ct::TreeView view() const {
         ct::TreeView v;
@@ -246,6 +272,13 @@ struct ct_tree {
         for (int k = 0; k < 4; k++) v.bbox[k] = bbox[k];
         v.elem_xy = elem_xy;
         v.treelets = treelets;
+        v.entry.handle = entry_handle;
+        v.entry.lo = entry_lo;
+        v.entry.bits = entry_bits;
+        v.entry.xmin = bbox[0];
+        v.entry.ymin = bbox[2];
+        v.entry.sx = grid_sx;
+        v.entry.sy = grid_sy;
         return v;
     }
 };

@@ -48,11 +48,7 @@ __global__ void __launch_bounds__(256) k_morton_keys(const double *__restrict__ 
             y = 0.5 * (a.y + b.y);
         }
     }
-    double fx = (x - xmin) * sx, fy = (y - ymin) * sy;  // [0, 65536) inside the tree's bounding box
-    fx = fx >= 0.0 ? fx : 0.0;                          // also catches NaN
-    fy = fy >= 0.0 ? fy : 0.0;
-    uint32_t ix = fx < 65535.0 ? (uint32_t)fx : 65535u;
-    uint32_t iy = fy < 65535.0 ? (uint32_t)fy : 65535u;
+    const uint32_t ix = grid_coord(x, xmin, sx), iy = grid_coord(y, ymin, sy);  // [0, 65536) inside the tree's bounding box
     keys[i] = (spread16(ix) | (spread16(iy) << 1)) >> shift;
     idx[i] = (uint32_t)i;
 }
@@ -86,8 +82,7 @@ struct MortonOrder {
         CT_CHECK(keys_b.alloc(n, s));
         CT_CHECK(idx_a.alloc(n, s));
         CT_CHECK(idx_b.alloc(n, s));
-        double wx = tree->bbox[1] - tree->bbox[0], wy = tree->bbox[3] - tree->bbox[2];
-        double sx = wx > 0 ? 65536.0 / wx : 0.0, sy = wy > 0 ? 65536.0 / wy : 0.0;
+        const double sx = tree->grid_sx, sy = tree->grid_sy;
         k_morton_keys<KIND><<<grid_for(n, 256), 256, 0, s>>>(q, n, tree->bbox[0], tree->bbox[2], sx, sy, 32 - bits, keys_a.p, idx_a.p);
         CT_LAUNCH_CHECK();
         cub::DoubleBuffer<uint32_t> d_keys(keys_a.p, keys_b.p);

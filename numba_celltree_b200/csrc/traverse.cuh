@@ -70,6 +70,15 @@ CT_DEV void cursor_descend(Cursor &c, const char *__restrict__ base, uint32_t ch
         cursor_enter(c, base, child);
     }
 }
+// where the descent of a point query starts (common.cuh: EntryGrid)
+CT_DEV uint32_t entry_handle(const EntryGrid &g, P2 p) {
+    if (g.handle == nullptr) return ROOT_HANDLE;
+    const int shift = 16 - g.bits;
+    const uint32_t cx = grid_coord(p.x, g.xmin, g.sx) >> shift, cy = grid_coord(p.y, g.ymin, g.sy) >> shift;
+    const bool inside = p.x > __ldg(g.lo + cx) && p.y > __ldg(g.lo + (1 << g.bits) + cy);  // false for NaN
+    return inside ? __ldg(g.handle + ((cy << g.bits) | cx)) : ROOT_HANDLE;
+}
+
 CT_DEV int4 cursor_leaf(const Cursor &c) {  // {ptr, size, id0, id1}
     const long long a = __double_as_longlong(c.plane.x), b = __double_as_longlong(c.plane.y);
     return make_int4((int)(a & 0xffffffffLL), (int)(a >> 32), (int)(b & 0xffffffffLL), (int)(b >> 32));
@@ -90,7 +99,7 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
     int sp = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, ROOT_HANDLE);
+    cursor_enter(c, base, entry_handle(t.entry, p));
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;
@@ -138,7 +147,7 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
     int sp = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, ROOT_HANDLE);
+    cursor_enter(c, base, entry_handle(t.entry, p));
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;

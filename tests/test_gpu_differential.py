@@ -72,6 +72,35 @@ def test_points_and_weights(delaunay_pair):
         assert np.array_equal(w, rw)
 
 
+def test_points_on_planes_and_entry_grid_boundaries(pkg):
+    """Points exactly on split planes / cell corners / entry-grid cell boundaries, and one ulp to either side."""
+    for nx, ny in ((64, 64), (96, 40)):
+        vertices, faces = quad_mesh(nx, ny)
+        tree = pkg.CellTree2d(vertices, faces, -1)
+        ref = oracle.CellTree2d(vertices, faces, -1)
+        xs = np.unique(np.concatenate([vertices[:, 0], 0.5 * (vertices[:-1, 0] + vertices[1:, 0])]))
+        ys = np.unique(np.concatenate([vertices[:, 1], np.linspace(0, 1, 4 * ny + 1)]))
+        xs = np.concatenate([xs, np.nextafter(xs, -np.inf), np.nextafter(xs, np.inf), [-0.25, 1.25, np.inf, -np.inf, np.nan]])
+        ys = np.concatenate([ys, np.nextafter(ys, -np.inf), np.nextafter(ys, np.inf), [-0.25, 1.25, np.inf, -np.inf, np.nan]])
+        xx, yy = np.meshgrid(xs, ys)
+        points = np.column_stack((xx.ravel(), yy.ravel()))
+        for tolerance in (None, 0.0, 1e-9):
+            got = tree.locate_points(points, tolerance)
+            want = ref.locate_points(points, tolerance)
+            assert np.array_equal(got, want)
+    # an irregular mesh: the same kinds of points around its vertex coordinates
+    vertices, faces = delaunay_mesh(4_000, seed=21)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    rng = np.random.default_rng(8)
+    pick = vertices[rng.integers(0, len(vertices), 20_000)]
+    points = np.concatenate([pick, np.nextafter(pick, -np.inf), np.nextafter(pick, np.inf), np.column_stack((pick[:, 0], pick[::-1, 1]))])
+    assert np.array_equal(tree.locate_points(points), ref.locate_points(points))
+    i, w = tree.compute_barycentric_weights(points)
+    ri, rw = ref.compute_barycentric_weights(points)
+    assert np.array_equal(i, ri) and np.array_equal(w, rw)
+
+
 def test_morton_ordering_is_invisible(pkg, delaunay_pair):
     from numba_celltree_b200 import _lib
 
