@@ -161,6 +161,22 @@ def test_edges(delaunay_pair):
     assert np.array_equal(xy, rxy, equal_nan=True)
 
 
+def test_edges_with_a_short_or_absent_hit_log(pkg, delaunay_pair):
+    """The hit log is an execution detail: overflowing it (or having none) falls back to the second traversal."""
+    from numba_celltree_b200 import _lib
+
+    tree, ref, _, faces = delaunay_pair
+    edges = c4_edges(len(faces), 200_000)
+    ri, rj, rxy = ref.intersect_edges(edges)
+    try:
+        for per_segment in (0, 1, 12):
+            _lib.check(_lib.load().ct_set_edge_log(per_segment))
+            i, j, xy = tree.intersect_edges(edges)
+            assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(xy, rxy, equal_nan=True)
+    finally:
+        _lib.check(_lib.load().ct_set_edge_log(-1))
+
+
 def test_faces_and_self_intersection(delaunay_pair):
     tree, ref, vertices, faces = delaunay_pair
     qv, qf = quad_mesh(150, 150)
