@@ -178,13 +178,20 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         return locate_points_device(tree, reinterpret_cast<const double2 *>(points), n, tolerance, out_index, weights, s, true);
 
     // host buffers: chunked pipeline on two private streams (copy-in / kernel / copy-out overlap)
-    const int64_t CHUNK = 1 << 22;
-    const int NS = 2;
+    // three streams: while one chunk is being copied in, the previous two may still be computing / copying out, so
+    // the host-to-device copy engine -- the bottleneck of this path -- never waits for a stream to come free
+    static int64_t CHUNK = 0;
+    if (CHUNK == 0) {
+        const char *e = getenv("CELLTREE_HOST_CHUNK");
+        CHUNK = e ? atoll(e) : (1 << 22);
+        if (CHUNK < 1024) CHUNK = 1024;
+    }
+    constexpr int NS = 3;
     const int M = tree->M;
     cudaStream_t st[NS];
-    double2 *d_pts[NS] = {nullptr, nullptr};
-    int64_t *d_out[NS] = {nullptr, nullptr};
-    double *d_w[NS] = {nullptr, nullptr};
+    double2 *d_pts[NS] = {};
+    int64_t *d_out[NS] = {};
+    double *d_w[NS] = {};
     const int64_t chunk = n < CHUNK ? (n > 0 ? n : 1) : CHUNK;
     int status = CT_OK;
     CT_CUDA(cudaStreamSynchronize(s));

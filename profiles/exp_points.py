@@ -34,3 +34,12 @@ lib.ct_profile_enable(0)
 print(os.environ.get("CELLTREE_B200_LIB", "default").split("/")[-1], "ms/step %.3f" % (e0.elapsed_time(e1) / 5),
       "Gq/s %.3f" % (n / (e0.elapsed_time(e1) / 5) / 1e6), "order %.3f traverse %.3f" % (a.value, b.value),
       "build %.1f ms" % tree2.build_ms, "checksum", int(out.sum().item()))
+
+if os.environ.get("WEIGHTS", "1") != "0":
+    for _ in range(2): r = tree.compute_barycentric_weights(pts)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3): r = tree.compute_barycentric_weights(pts)
+    e1.record(); torch.cuda.synchronize()
+    print("compute_barycentric_weights ms/step %.3f" % (e0.elapsed_time(e1) / 3), "Gq/s %.3f" % (n / (e0.elapsed_time(e1) / 3) / 1e6),
+          "weights checksum %.9f" % float(r[1].sum().item()))
