@@ -12,7 +12,8 @@ One "step" = one locate_points pass over the whole batch.
   e2e        the same call through the public API with HOST (pinned) buffers: host->device copy of the
              points and device->host copy of the indices inside the timed region.
   roofline   dominant kernel (k_locate_points): algorithmic bytes (918 B/query at C2) x queries
-             / its launch duration (CUDA events on the launching stream), against the measured HBM copy peak.
+             / its launch duration (CUDA events on the launching stream), against the measured HBM copy peak;
+             `traffic` is that kernel's DRAM bytes per launch from the ncu capture named in profiles/traffic.json.
   cpu_baseline  the CPU oracle (C restatement of the reference's algorithm, OpenMP over queries like the
              reference's prange) timed on this box's host cores on a bounded prefix of the same points.
 
@@ -320,7 +321,7 @@ def main():
     achieved = ALGORITHMIC_BYTES_PER_QUERY * n_points / (kernel_avg_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": "k_locate_points<4,false,9> (traversal + point-in-polygon; one launch per step)",
+        "kernel": "k_locate_points<4,false,9> (entry grid + treelet descent + point-in-polygon; one launch per step)",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -331,15 +332,47 @@ def main():
         "kernel_ms": kernel_avg_ms,
         "kernel_share_of_step": kernel_avg_ms / ms_per_step,
         "morton_order_ms": order_avg_ms,
+        "unpermute_ms": ms_per_step - order_avg_ms - kernel_avg_ms,
         "step_achieved": ALGORITHMIC_BYTES_PER_QUERY * n_points / (ms_per_step * 1e-3) / 1e9,
         "step_frac": ALGORITHMIC_BYTES_PER_QUERY * n_points / (ms_per_step * 1e-3) / 1e9 / peak,
     }
     traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists():
+    if traffic_file.exists() and n_points == 100_000_000 and nx == 4096:
         try:
             roofline["traffic"] = json.loads(traffic_file.read_text()).get("k_locate_points_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/traffic.json (ncu --set full of this kernel on this workload)"
+            roofline["dram_gbs"] = roofline["traffic"] / (kernel_avg_ms * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_gbs"] / peak
         except Exception:
             pass
+    roofline["note"] = (
+        "frac counts SURVEY 8d's algorithmic bytes (24 node visits x 32 B + cells + point + result per query); most of them "
+        "are served by L1/L2 after Morton ordering or skipped by the entry grid, so frac > 1 is not a DRAM rate -- dram_frac "
+        "(ncu DRAM bytes / launch time / peak) is; the kernel is issue- and latency-bound"
+    )
+
+    # ---- the other half of config C2: locate_points + barycentric (Wachspress) weights, device-resident ---------------------
+    weights_line = None
+    if rank == 0 and world == 1:
+        for _ in range(2):
+            tree.compute_barycentric_weights(dev_points)
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        w = None
+        for _ in range(3):
+            del w  # free the previous result first: the allocator then reuses its block instead of growing
+            _, w = tree.compute_barycentric_weights(dev_points)
+        w1.record()
+        torch.cuda.synchronize()
+        w_ms = w0.elapsed_time(w1) / 3
+        weights_line = {
+            "metric": "compute_barycentric_weights queries/s (device-resident)",
+            "value": n_points / (w_ms * 1e-3),
+            "ms_per_step": w_ms,
+            "weights_row_sum_mean": float(w.sum().item()) / n_points,
+        }
+        del w
 
     # ---- end to end through the public API with pinned host buffers --------------------------------------------------
     out_np = host_out.numpy()
@@ -416,6 +449,7 @@ def main():
             "parity": parity,
             "e2e_equals_device_result": same,
             "secondary": secondary,
+            "barycentric_weights": weights_line,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
