@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(BLOCK) k_box_area(TreeView t, const double *__
     box_polygon(load_box(boxes, pi[k]), a);
     Poly<MAXB> b;
     load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
-    double ar = polygon_polygon_clip_area<4, MAXB>(a, b);
+    double ar = clip_area_of_pair<4, MAXB, BLOCK>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;
 }
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip_area(TreeView t, const int32_t *
     gather_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
     Poly<MAXB> b;
     load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
-    double ar = polygon_polygon_clip_area<MAXA, MAXB>(a, b);
+    double ar = clip_area_of_pair<MAXA, MAXB, BLOCK>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;
 }

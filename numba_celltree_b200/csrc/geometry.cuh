@@ -412,16 +412,32 @@ CT_DEV bool sh_intersection(P2 a, P2 V, P2 r, P2 N, P2 &out) {  // :63-74
     return false;
 }
 
-// polygon_area, geometry_utils.py:82-95 (fan triangulation, abs of each cross product)
+// Working storage of the clip: two polygons of CAP vertices that swap roles after every clip edge.
+// Small bounds live in shared memory, vertex-major with the block's threads innermost ([2][CAP][threads] double2:
+// conflict-free 16-byte accesses); as per-thread arrays they would be indexed dynamically and end up in local
+// memory, whose traffic through L1/L2 was what bound the pair kernels (234 GB of L2 sectors per 126 M pairs).
 template <int CAP>
-CT_DEV double polygon_area(const double (&px)[CAP], const double (&py)[CAP], int length) {
+struct SharedClipWork {
+    double2 *base;  // this thread's first element
+    int stride;     // threads per block
+    CT_DEV double2 &at(int buffer, int j) const { return base[(buffer * CAP + j) * stride]; }
+};
+template <int CAP>
+struct LocalClipWork {
+    double2 v[2][CAP];
+    CT_DEV double2 &at(int buffer, int j) { return v[buffer][j]; }
+};
+
+// polygon_area, geometry_utils.py:82-95 (fan triangulation, abs of each cross product)
+template <typename Work>
+CT_DEV double polygon_area(Work &work, int buffer, int length) {
     double area = 0.0;
-    P2 a{px[0], py[0]};
-    P2 b{px[1], py[1]};
-    P2 U = to_vector(a, b);
+    const double2 a2 = work.at(buffer, 0), b2 = work.at(buffer, 1);
+    P2 a{a2.x, a2.y};
+    P2 U = to_vector(a, P2{b2.x, b2.y});
     for (int i = 2; i < length; i++) {
-        P2 c{px[i], py[i]};
-        P2 V = to_vector(c, a);
+        const double2 c2 = work.at(buffer, i);
+        P2 V = to_vector(P2{c2.x, c2.y}, a);
         area += fabs(cross_product(U, V));
         U = V;
     }
@@ -431,16 +447,17 @@ CT_DEV double polygon_area(const double (&px)[CAP], const double (&py)[CAP], int
 // polygon_polygon_clip_area, sutherland_hodgman.py:84-148: clip `polygon` (subject) by every edge of
 // `clipper`; zero-length clipper / subject edges are skipped; early 0.0 when fewer than 3 vertices remain.
 // The working polygons hold at most MAXA + MAXB vertices (a convex subject gains at most one vertex per
-// clip edge); the reference sizes them 2 * MAX_N_VERTEX = 64.
-template <int MAXA, int MAXB>
-CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MAXB> &clipper) {
+// clip edge); the reference sizes them 2 * MAX_N_VERTEX = 64 and copies the output back into the subject
+// after every clip edge, here the two buffers swap roles.
+template <int MAXA, int MAXB, typename Work>
+CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MAXB> &clipper, Work &work) {
     constexpr int CAP = MAXA + MAXB;
-    double sx[CAP], sy[CAP], ox[CAP], oy[CAP];
     int n_output = polygon.n;
     const int n_clip = clipper.n;
+    int out = 0;  // buffer that holds the current output polygon
 #pragma unroll
     for (int i = 0; i < MAXA; i++)
-        if (i < n_output) { ox[i] = polygon.x[i]; oy[i] = polygon.y[i]; }
+        if (i < n_output) work.at(out, i) = make_double2(polygon.x[i], polygon.y[i]);
 
     P2 r = pget(clipper, n_clip - 1);
 #pragma unroll
@@ -450,29 +467,38 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
         P2 U{s.x - r.x, s.y - r.y};
         if (U.x == 0 && U.y == 0) continue;
         P2 N{-U.y, U.x};
-        int length = n_output;
-        for (int j = 0; j < length; j++) { sx[j] = ox[j]; sy[j] = oy[j]; }
+        const int length = n_output;
+        const int in = out;  // the previous output is the subject of this clip edge
+        out ^= 1;
         n_output = 0;
-        P2 a{sx[length - 1], sy[length - 1]};
+        auto push = [&](P2 v) {
+            if (n_output < CAP) {
+                work.at(out, n_output) = make_double2(v.x, v.y);
+                n_output++;
+            }
+        };
+        const double2 last = work.at(in, length - 1);
+        P2 a{last.x, last.y};
         bool a_inside = sh_inside(a, r, U);
         for (int j = 0; j < length; j++) {
-            P2 b{sx[j], sy[j]};
+            const double2 b2 = work.at(in, j);
+            P2 b{b2.x, b2.y};
             P2 V{b.x - a.x, b.y - a.y};
             if (V.x == 0 && V.y == 0) continue;
             bool b_inside = sh_inside(b, r, U);
             if (b_inside) {
                 if (!a_inside) {
                     P2 point;
-                    if (sh_intersection(a, V, r, N, point) && n_output < CAP) { ox[n_output] = point.x; oy[n_output] = point.y; n_output++; }
+                    if (sh_intersection(a, V, r, N, point)) push(point);
                 }
-                if (n_output < CAP) { ox[n_output] = b.x; oy[n_output] = b.y; n_output++; }
+                push(b);
             } else if (a_inside) {
                 P2 point;
                 if (sh_intersection(a, V, r, N, point)) {
-                    if (n_output < CAP) { ox[n_output] = point.x; oy[n_output] = point.y; n_output++; }
+                    push(point);
                 } else {
                     b_inside = true;
-                    if (n_output < CAP) { ox[n_output] = b.x; oy[n_output] = b.y; n_output++; }
+                    push(b);
                 }
             }
             a = b;
@@ -481,7 +507,22 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
         if (n_output < 3) return 0.0;
         r = s;
     }
-    return polygon_area(ox, oy, n_output);
+    return polygon_area(work, out, n_output);
+}
+
+// The per-pair kernels' entry: shared-memory working polygons for the small bounds, per-thread arrays otherwise.
+// THREADS = threads per block of the calling kernel.
+template <int MAXA, int MAXB, int THREADS>
+CT_DEV double clip_area_of_pair(const Poly<MAXA> &a, const Poly<MAXB> &b) {
+    constexpr int CAP = MAXA + MAXB;
+    if constexpr (CAP <= 8) {
+        __shared__ double2 storage[2 * CAP * THREADS];
+        SharedClipWork<CAP> work{storage + threadIdx.x, THREADS};
+        return polygon_polygon_clip_area<MAXA, MAXB>(a, b, work);
+    } else {
+        LocalClipWork<CAP> work;
+        return polygon_polygon_clip_area<MAXA, MAXB>(a, b, work);
+    }
 }
 
 // ---- separating axis test: algorithms/separating_axis.py -----------------------------------------------

@@ -103,24 +103,12 @@ template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
                                 const uint32_t *perm, int32_t *in_order, cudaStream_t s) {
     int grid = grid_for(n, PER_THREAD * BLOCK);
-    // 56 registers (9 blocks of 128 threads per SM) instead of 64: the traversal is latency-bound and one more
-    // resident block per SM is worth the handful of spilled values; tighter caps spill into the hot loop and
-    // lose (measured on C2, ms per 100 M points: 64 regs 12.7, 56 regs 11.9, 48 regs 14.7, 40 regs 17.3).
-    static int minb = -1;
-    if (minb < 0) {
-        const char *e = getenv("CELLTREE_POINTS_MINB");
-        minb = e ? atoi(e) : 9;
-    }
+    // 56 registers (9 blocks of 128 threads per SM) for the 3- and 4-vertex kernels: measured on C2, ms per 100 M points,
+    // 64 regs 6.62, 56 regs 6.55, 48 regs 6.57, 40 regs 6.82 -- the cap hardly matters since the descent loop is lean
     if (weights)
         k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
-    else if (MAXV <= 4 && minb == 9)
+    else if (MAXV <= 4)
         k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
-#ifdef CT_EXPERIMENT_MINB
-    else if (MAXV == 4 && minb == 10)
-        k_locate_points<4, false, 10><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
-    else if (MAXV == 4 && minb == 12)
-        k_locate_points<4, false, 12><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
-#endif
     else
         k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
     CT_LAUNCH_CHECK();

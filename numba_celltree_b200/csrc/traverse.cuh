@@ -16,10 +16,6 @@
 
 namespace ct {
 
-#ifndef CT_LEAF_PREFETCH
-#define CT_LEAF_PREFETCH 0
-#endif
-
 constexpr int STACK_CAP = 64;
 
 constexpr int LEAF_INLINE = 2;  // element ids stored with a leaf position of a treelet
@@ -123,13 +119,6 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
             }
         }
         const int4 leaf = cursor_leaf(c);
-#if CT_LEAF_PREFETCH
-        if (leaf.y > 1) {  // the second cell's polygon is on its way while the first is tested
-            const char *row = reinterpret_cast<const char *>(t.elem_xy + (int64_t)leaf.w * t.M);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
-            if (MAXV > 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 32));
-        }
-#endif
         for (int k = 0; k < leaf.y; k++) {
             int bbox_index = leaf_element(leaf, t.bb_indices, k);
             Poly<MAXV> poly;
