@@ -80,7 +80,7 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_void_p)],
     ),
     "ct_intersect_edges": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, ctypes.POINTER(c_void_p)]),
-    "ct_set_edge_log": (ctypes.c_int, [c_i64]),
+    "ct_set_hit_log": (ctypes.c_int, [c_i64]),
     "ct_result_size": (c_i64, [c_void_p]),
     "ct_result_payload_width": (c_i32, [c_void_p]),
     "ct_result_fetch": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32]),

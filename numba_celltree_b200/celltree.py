@@ -62,25 +62,8 @@ class CellTree2d(CellTree2dBase):
     @classmethod
     def from_arrays(cls, vertices, faces, nodes, bb_indices, bb_coords, cells_per_leaf: int = 2, n_buckets: int = 4):
         """Upload a tree whose arrays were built elsewhere (``faces`` already counter-clockwise, -1 filled)."""
-        self = cls.__new__(cls)
-        vertices = cast_vertices(vertices, copy=True)
         faces = cast_faces(faces, -1)
-        nodes = np.ascontiguousarray(nodes, dtype=NodeDType)
-        bb_indices = np.ascontiguousarray(bb_indices, dtype=IntDType)
-        bb_coords = cast_bboxes(bb_coords)
-        handle = ctypes.c_void_p()
-        _lib.check(
-            _lib.load().ct_tree_from_arrays(
-                vertices.ctypes.data, vertices.shape[0], faces.ctypes.data, faces.shape[0], faces.shape[1],
-                _lib.CT_KIND_FACES, nodes.ctypes.data, len(nodes), bb_indices.ctypes.data, bb_coords.ctypes.data,
-                int(cells_per_leaf), _lib.CT_MEM_HOST, ctypes.byref(handle),
-            )
-        )  # fmt: skip
-        self._tree = DeviceTree(handle.value)
-        self.vertices = vertices
-        self.n_buckets = n_buckets
-        self.cells_per_leaf = cells_per_leaf
-        return self
+        return cls._from_arrays(vertices, faces, nodes, bb_indices, bb_coords, cells_per_leaf, n_buckets, _lib.CT_KIND_FACES)
 
     @property
     def faces(self):

@@ -6,6 +6,9 @@
 namespace ct {
 
 // ---- box kernels ---------------------------------------------------------------------------------------------
+// count -> scan -> fill: the traversal runs twice.  The candidate test is four comparisons, so a second traversal is
+// cheaper than logging the hits of the first (measured on C3: 14.2 ms against 16.5 ms with the hit log that
+// intersect_edges uses, whose candidate test is a clip).
 template <bool FILL>
 __global__ void __launch_bounds__(BLOCK) k_locate_boxes(TreeView t, const double *__restrict__ boxes, int64_t n,
                                                         int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,

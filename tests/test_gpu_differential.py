@@ -161,20 +161,24 @@ def test_edges(delaunay_pair):
     assert np.array_equal(xy, rxy, equal_nan=True)
 
 
-def test_edges_with_a_short_or_absent_hit_log(pkg, delaunay_pair):
+def test_boxes_and_edges_with_a_short_or_absent_hit_log(pkg, delaunay_pair):
     """The hit log is an execution detail: overflowing it (or having none) falls back to the second traversal."""
     from numba_celltree_b200 import _lib
 
     tree, ref, _, faces = delaunay_pair
     edges = c4_edges(len(faces), 200_000)
+    boxes = c3_boxes(len(faces), 200_000)
     ri, rj, rxy = ref.intersect_edges(edges)
+    bi, bj, ba = ref.intersect_boxes(boxes)
     try:
-        for per_segment in (0, 1, 12):
-            _lib.check(_lib.load().ct_set_edge_log(per_segment))
+        for per_query in (0, 1, 16):
+            _lib.check(_lib.load().ct_set_hit_log(per_query))
             i, j, xy = tree.intersect_edges(edges)
             assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(xy, rxy, equal_nan=True)
+            i, j, a = tree.intersect_boxes(boxes)
+            assert np.array_equal(i, bi) and np.array_equal(j, bj) and np.array_equal(a, ba)
     finally:
-        _lib.check(_lib.load().ct_set_edge_log(-1))
+        _lib.check(_lib.load().ct_set_hit_log(-1))
 
 
 def test_faces_and_self_intersection(delaunay_pair):
@@ -245,6 +249,29 @@ def test_results_in_pinned_memory_equal_pageable_results(pkg, delaunay_pair):
     finally:
         _lib.set_pinned_results(True)
         _lib.load().ct_host_trim()
+
+
+def test_save_and_load_round_trip(pkg, delaunay_pair, tmp_path):
+    """A tree written to .npz and read back answers like the original (and refuses the other tree kind)."""
+    from numba_celltree_b200.synthetic import random_network
+
+    tree, ref, _, faces = delaunay_pair
+    tree.save(tmp_path / "faces.npz")
+    again = pkg.CellTree2d.load(tmp_path / "faces.npz")
+    assert_same_tree(again, ref)
+    points = np.random.default_rng(12).uniform(0, 1, (50_000, 2))
+    assert np.array_equal(again.locate_points(points), ref.locate_points(points))
+    edges = c4_edges(len(faces), 20_000)
+    for a, b in zip(again.intersect_edges(edges), ref.intersect_edges(edges)):
+        assert np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(ValueError):
+        pkg.EdgeCellTree2d.load(tmp_path / "faces.npz")
+    vertices, segments = random_network(5_000, seed=3)
+    net = pkg.EdgeCellTree2d(vertices, segments)
+    net.save(tmp_path / "network.npz")
+    net2 = pkg.EdgeCellTree2d.load(tmp_path / "network.npz")
+    assert np.array_equal(net2.nodes, net.nodes) and np.array_equal(net2.bb_indices, net.bb_indices)
+    assert np.array_equal(net2.locate_points(vertices[:2000]), net.locate_points(vertices[:2000]))
 
 
 def test_edge_network(pkg):
