@@ -7,51 +7,192 @@
 namespace ct {
 
 // ---- edge kernels ----------------------------------------------------------------------------------------------
-// The clip of a segment against a candidate cell (Cohen-Sutherland, then Cyrus-Beck) is by far the expensive part of
-// the traversal, so it is done ONCE: count + log, scan, place (hitlog.cuh); the second traversal (FILL) only runs
-// when the log overflows.
-enum { EDGES_COUNT_AND_LOG = 0, EDGES_FILL = 1 };
+// The clip of a segment against a candidate cell (Cohen-Sutherland, then Cyrus-Beck) is by far the expensive part, and
+// with one thread per segment doing everything the lanes of a warp are hardly ever at the same place (ncu: 4.2 of 32
+// lanes active per instruction).  The first pass is therefore WARP-COOPERATIVE:
+//   * every lane walks the tree for its own segment, one node per iteration, through one branch-free step
+//     (edge_plane_test + selects), and pushes the cells of the leaves it reaches -- with their ordinal in the
+//     segment's candidate sequence -- onto a queue in shared memory that the warp shares;
+//   * whenever the queue holds 32 candidates (or the walks are over), the 32 lanes clip one candidate each, whoever
+//     pushed it; a hit is appended to the log (hitlog.cuh) with the segment, the candidate's ordinal, the cell and the
+//     clipped points, and counted for its segment.
+// After the scan of the counts, k_place_hits_unordered drops every hit somewhere in its segment's range, and the final
+// per-segment sort orders the range by (t, ordinal): the reference's stable sort by t of the hits in emission order
+// (geometry_utils.py:564-574), since the ordinal grows with the emission order.
+// If the log overflows, the second traversal (one thread per segment, k_locate_edges_fill) writes the pairs in emission order.
+constexpr int QUEUE_CAP = 64;  // per warp: a step adds at most 32 candidates, a drain starts at 32
 
-template <int MAXV, int MODE>
-__global__ void __launch_bounds__(BLOCK) k_locate_edges(TreeView t, const double *__restrict__ edges, int64_t n,
-                                                        int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-                                                        int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
-                                                        double *__restrict__ out_xy, const uint32_t *__restrict__ perm, HitLog log) {
+template <int MAXV>
+__global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const double *__restrict__ edges, int64_t n,
+                                                             int32_t *__restrict__ counts, const uint32_t *__restrict__ perm,
+                                                             HitLog log) {
+    constexpr int WARPS = BLOCK / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double2 s_segment[WARPS][32][2];
+    __shared__ int32_t s_hits[WARPS][32];
+    __shared__ int32_t s_cell[WARPS][QUEUE_CAP], s_ordinal[WARPS][QUEUE_CAP];
+    __shared__ uint8_t s_owner[WARPS][QUEUE_CAP];
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = slot < n;
+    const int64_t q = valid ? (perm ? (int64_t)__ldg(perm + slot) : slot) : 0;
+    P2 a{0.0, 0.0}, b{0.0, 0.0};
+    if (valid) {
+        const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
+        const double2 a2 = __ldg(e), b2 = __ldg(e + 1);
+        a = P2{a2.x, a2.y};
+        b = P2{b2.x, b2.y};
+    }
+    s_segment[warp][lane][0] = make_double2(a.x, a.y);
+    s_segment[warp][lane][1] = make_double2(b.x, b.y);
+    s_hits[warp][lane] = 0;
+    bool active = false;
+    if (valid) {
+        P2 c, d;
+        Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
+        active = cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d) != 0;
+    }
+    const P2 V = to_vector(a, b);
+    const char *base = reinterpret_cast<const char *>(t.treelets);
+    uint32_t stack[STACK_CAP];
+    int sp = 0;
+    Cursor cur;
+    cursor_enter(cur, base, ROOT_HANDLE);
+    int leaf_k = 0;    // cells of the current leaf already pushed
+    int ordinal = 0;   // candidates of this segment pushed so far
+    int queued = 0;    // entries in the warp's queue (warp-uniform)
+    __syncwarp();
+    while (true) {
+        const bool walking = __any_sync(FULL, active);
+        if (!walking && queued == 0) break;
+        // ---- one node per walking lane ------------------------------------------------------------------------------
+        bool push = false;
+        int cell = 0;
+        if (active) {
+            uint32_t next = 0;
+            bool pop = false, move = true;
+            if (cursor_is_leaf(cur)) {
+                const int4 leaf = cursor_leaf(cur);
+                if (leaf_k < leaf.y) {
+                    cell = leaf_element(leaf, t.bb_indices, leaf_k);
+                    push = true;
+                    leaf_k++;
+                }
+                if (leaf_k >= leaf.y) {
+                    leaf_k = 0;
+                    pop = true;
+                } else {
+                    move = false;  // more cells of this leaf to push
+                }
+            } else {
+                bool left, right;
+                edge_plane_test(cur, a, b, V, left, right);
+                uint32_t left_handle, right_handle;
+                cursor_children(cur, left_handle, right_handle);
+                if (left && right) stack[sp++] = left_handle;
+                next = right ? right_handle : left_handle;
+                pop = !(left || right);
+            }
+            if (pop) {
+                if (sp == 0) {
+                    active = false;
+                    move = false;
+                } else {
+                    next = stack[--sp];
+                }
+            }
+            if (move) cursor_enter(cur, base, next);
+        }
+        // ---- candidates onto the warp's queue -------------------------------------------------------------------------
+        const unsigned pushing = __ballot_sync(FULL, push);
+        if (push) {
+            const int at = queued + __popc(pushing & ((1u << lane) - 1u));
+            s_cell[warp][at] = cell;
+            s_ordinal[warp][at] = ordinal++;
+            s_owner[warp][at] = (uint8_t)lane;
+        }
+        queued += __popc(pushing);
+        __syncwarp();
+        // ---- 32 candidates at a time, one per lane ----------------------------------------------------------------
+        const bool last = !__any_sync(FULL, active);
+        while (queued >= 32 || (last && queued > 0)) {
+            const int take = queued < 32 ? queued : 32;
+            const int first = queued - take;
+            const bool mine = (int)lane < take;
+            const int owner = mine ? s_owner[warp][first + lane] : (int)lane;
+            const int64_t owner_q = __shfl_sync(FULL, q, owner);
+            if (mine) {
+                const int bbox_index = s_cell[warp][first + lane];
+                const double2 a2 = s_segment[warp][owner][0], b2 = s_segment[warp][owner][1];
+                P2 c, d;
+                if (edge_cell_intersect<MAXV>(t, bbox_index, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d)) {
+                    const int64_t at = hitlog_reserve(log);
+                    if (at < log.capacity) {
+                        log.q[at] = (int32_t)owner_q;
+                        log.k[at] = s_ordinal[warp][first + lane];
+                        log.j[at] = bbox_index;
+                        double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
+                        o[0] = make_double2(c.x, c.y);
+                        o[1] = make_double2(d.x, d.y);
+                    }
+                    atomicAdd(&s_hits[warp][owner], 1);
+                }
+            }
+            queued = first;
+            __syncwarp();
+        }
+    }
+    if (valid) counts[q] = s_hits[warp][lane];
+}
+
+// log entry -> some free place of its segment's range (the sort orders the range); `ordinal` keeps what the sort needs
+__global__ void __launch_bounds__(256) k_place_hits_unordered(HitLog log, int64_t entries, const int64_t *__restrict__ offsets,
+                                                              int32_t *__restrict__ filled, int32_t *__restrict__ out_i,
+                                                              int32_t *__restrict__ out_j, double *__restrict__ out_xy,
+                                                              int32_t *__restrict__ ordinal) {
+    int64_t at = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (at >= entries) return;
+    const int32_t q = __ldcs(log.q + at);
+    const int64_t to = offsets[q] + atomicAdd(filled + q, 1);
+    out_i[to] = q;
+    out_j[to] = __ldcs(log.j + at);
+    ordinal[to] = __ldcs(log.k + at);
+    const double2 *in = reinterpret_cast<const double2 *>(log.xy + 4 * at);
+    double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
+    o[0] = __ldcs(in);
+    o[1] = __ldcs(in + 1);
+}
+
+// the second traversal, one thread per segment: pairs in emission order (their ordinal is their rank)
+template <int MAXV>
+__global__ void __launch_bounds__(BLOCK) k_locate_edges_fill(TreeView t, const double *__restrict__ edges, int64_t n,
+                                                             const int64_t *__restrict__ offsets, int32_t *__restrict__ out_i,
+                                                             int32_t *__restrict__ out_j, double *__restrict__ out_xy,
+                                                             int32_t *__restrict__ ordinal, const uint32_t *__restrict__ perm) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (q >= n) return;
     if (perm) q = __ldg(perm + q);  // execution order only
     const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
     double2 a2 = __ldg(e), b2 = __ldg(e + 1);
     P2 a{a2.x, a2.y}, b{b2.x, b2.y};
-    if constexpr (MODE == EDGES_FILL) {
-        int64_t base = offsets[q];
-        locate_edge<MAXV>(t, a, b, [&](int k, int bbox_index, P2 c, P2 d) {
-            out_i[base + k] = (int32_t)q;
-            out_j[base + k] = bbox_index;
-            double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * (base + k));
-            o[0] = make_double2(c.x, c.y);
-            o[1] = make_double2(d.x, d.y);
-        });
-    } else {
-        counts[q] = locate_edge<MAXV>(t, a, b, [&](int k, int bbox_index, P2 c, P2 d) {
-            const int64_t at = hitlog_reserve(log);
-            if (at < log.capacity) {
-                log.q[at] = (int32_t)q;
-                log.k[at] = k;
-                log.j[at] = bbox_index;
-                double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
-                o[0] = make_double2(c.x, c.y);
-                o[1] = make_double2(d.x, d.y);
-            }
-        });
-    }
+    const int64_t base = offsets[q];
+    locate_edge<MAXV>(t, a, b, [&](int k, int bbox_index, P2 c, P2 d) {
+        out_i[base + k] = (int32_t)q;
+        out_j[base + k] = bbox_index;
+        ordinal[base + k] = k;
+        double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * (base + k));
+        o[0] = make_double2(c.x, c.y);
+        o[1] = make_double2(d.x, d.y);
+    });
 }
 
-// sort_intersections_by_edge, geometry_utils.py:564-574: within each query edge's (already contiguous)
-// range, stable sort by t = (c - a) . (b - a); np.lexsort puts NaN last and keeps ties in input order.
+// sort_intersections_by_edge, geometry_utils.py:564-574: within each query edge's (contiguous) range, the
+// reference's np.lexsort((t, edge)) is a stable sort by t = (c - a) . (b - a) of the hits in emission order, NaN last.
+// The range arrives in no particular order with the emission ordinal of every hit: sorting by (t, ordinal) is the same.
 __global__ void __launch_bounds__(BLOCK) k_sort_edge_ranges(const double *__restrict__ edges, int64_t n,
                                                             const int64_t *__restrict__ offsets, int32_t *__restrict__ out_j,
-                                                            double *__restrict__ out_xy) {
+                                                            double *__restrict__ out_xy, int32_t *__restrict__ ordinal) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (q >= n) return;
     int64_t lo = offsets[q], hi = offsets[q + 1];
@@ -61,24 +202,31 @@ __global__ void __launch_bounds__(BLOCK) k_sort_edge_ranges(const double *__rest
     double abx = b.x - a.x, aby = b.y - a.y;
     double2 *xy = reinterpret_cast<double2 *>(out_xy);
     auto t_of = [&](double2 c) { return (c.x - a.x) * abx + (c.y - a.y) * aby; };
-    auto lt = [](double x, double y) { return x < y || (y != y && x == x); };
+    // (x, ox) before (y, oy): smaller t first, NaN after every number, ties and NaNs by ordinal
+    auto before = [](double x, int ox, double y, int oy) {
+        if (x < y || (y != y && x == x)) return true;
+        if (y < x || (x != x && y == y)) return false;
+        return ox < oy;
+    };
     for (int64_t k = lo + 1; k < hi; k++) {
         double2 c = xy[2 * k], d = xy[2 * k + 1];
-        int32_t j = out_j[k];
+        int32_t j = out_j[k], o = ordinal[k];
         double tk = t_of(c);
         int64_t m = k;
         while (m > lo) {
             double2 cp = xy[2 * (m - 1)];
-            if (!lt(tk, t_of(cp))) break;
+            if (!before(tk, o, t_of(cp), ordinal[m - 1])) break;
             xy[2 * m] = cp;
             xy[2 * m + 1] = xy[2 * (m - 1) + 1];
             out_j[m] = out_j[m - 1];
+            ordinal[m] = ordinal[m - 1];
             m--;
         }
         if (m != k) {
             xy[2 * m] = c;
             xy[2 * m + 1] = d;
             out_j[m] = j;
+            ordinal[m] = o;
         }
     }
 }
@@ -110,8 +258,7 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     CT_CHECK(buffers.alloc(n, hit_log_per_query(), true, s));
     const HitLog &log = buffers.log;
     if (n > 0) {
-        k_locate_edges<MAXV, EDGES_COUNT_AND_LOG><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, nullptr, nullptr, nullptr,
-                                                                                      nullptr, order.perm, log);
+        k_edges_cooperative<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -121,14 +268,18 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     r->size = total;
     r->width = 4;
     if (n > 0 && total > 0) {
+        Scratch<int32_t> ordinal;
+        CT_CHECK(ordinal.alloc(total, s));
         if (total <= log.capacity) {
-            k_place_hits<<<grid_for(total, 256), 256, 0, s>>>(log, total, offsets.p, r->i, r->j, r->payload);
+            CT_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)n, s));  // reused as per-segment fill counters
+            k_place_hits_unordered<<<grid_for(total, 256), 256, 0, s>>>(log, total, offsets.p, counts.p, r->i, r->j, r->payload,
+                                                                       ordinal.p);
         } else {
-            k_locate_edges<MAXV, EDGES_FILL><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, nullptr, offsets.p, r->i, r->j,
-                                                                                 r->payload, order.perm, log);
+            k_locate_edges_fill<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
+                                                                          ordinal.p, order.perm);
         }
         CT_LAUNCH_CHECK();
-        k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload);
+        k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload, ordinal.p);
         CT_LAUNCH_CHECK();
     }
     CT_CUDA(cudaStreamSynchronize(s));

@@ -246,7 +246,35 @@ CT_DEV bool edge_edge_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
 }
 
 // ---- locate_edge, query.py:357-455 --------------------------------------------------------------------------
+// Which children of the inner node under the cursor the segment a -> b (V = b - a) may reach: the parametric test of
+// the planes Lmax / Rmin along the segment, query.py:407-440.  Written without branches (both quotients are always
+// formed and then selected) so that the lanes of a warp stay together; the values are those of the reference's
+// nested ifs: a quotient is only USED under the conditions under which the reference computes it.
+CT_DEV void edge_plane_test(const Cursor &cur, P2 a, P2 b, P2 V, bool &left, bool &right) {
+    const bool dim = cursor_dim(cur);
+    const double Lmax = cur.plane.x, Rmin = cur.plane.y;
+    const double dx = dim ? V.y : V.x;
+    const double a_d = dim ? a.y : a.x;
+    const double b_d = dim ? b.y : b.x;
+    const bool forward = dx > 0.0, backward = dx < 0.0;
+    const double dx_left = Lmax - (forward ? a_d : b_d);
+    const double dx_right = Rmin - (forward ? b_d : a_d);
+    const double t_left = dx_left / dx, t_right = dx_right / dx;
+    const bool left_t = forward ? (t_left >= 0.0) : (backward ? ((1.0 - t_left) >= 0.0) : true);
+    const bool right_t = forward ? (t_right <= 1.0) : (backward ? ((1.0 - t_right) <= 1.0) : true);
+    left = (dx_left >= 0.0) && left_t;
+    right = (dx_right <= 0.0) && right_t;
+}
+
 // MAXV == 0 selects the edge-edge test (EdgeCellTree2d), otherwise the edge-face test with that polygon bound.
+template <int MAXV>
+CT_DEV bool edge_cell_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P2 &c, P2 &d) {
+    if constexpr (MAXV == 0) return edge_edge_intersect(t, bbox_index, a, b, c, d);
+    else return edge_face_intersect<MAXV>(t, bbox_index, a, b, c, d);
+}
+
+// One thread walks one segment and tests every candidate as it meets it (the second traversal of the count -> fill
+// scheme; the first pass is the warp-cooperative kernel of edges.cu).
 template <int MAXV, typename Emit>
 CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
     {
@@ -262,58 +290,33 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
     Cursor cur;
     cursor_enter(cur, base, ROOT_HANDLE);
     while (true) {
-        while (!cursor_is_leaf(cur)) {
-            // parametric test of the planes Lmax / Rmin along the segment, query.py:407-440
-            const bool dim = cursor_dim(cur);
-            const double Lmax = cur.plane.x, Rmin = cur.plane.y;
-            double dx = dim ? V.y : V.x;
-            double a_d = dim ? a.y : a.x;
-            double b_d = dim ? b.y : b.x;
-            double dx_left, dx_right;
-            if (dx > 0.0) {
-                dx_left = Lmax - a_d;
-                dx_right = Rmin - b_d;
-            } else {
-                dx_left = Lmax - b_d;
-                dx_right = Rmin - a_d;
+        uint32_t next = 0;
+        bool pop;
+        if (cursor_is_leaf(cur)) {
+            const int4 leaf = cursor_leaf(cur);
+            for (int k = 0; k < leaf.y; k++) {
+                int bbox_index = leaf_element(leaf, t.bb_indices, k);
+                P2 c, d;
+                if (edge_cell_intersect<MAXV>(t, bbox_index, a, b, c, d)) {
+                    emit(count, bbox_index, c, d);
+                    count++;
+                }
             }
-            bool left = dx_left >= 0.0;
-            bool right = dx_right <= 0.0;
-            if (dx > 0.0) {
-                if (left) left = (dx_left / dx) >= 0.0;
-                if (right) right = (dx_right / dx) <= 1.0;
-            } else if (dx < 0.0) {
-                if (left) left = (1.0 - (dx_left / dx)) >= 0.0;
-                if (right) right = (1.0 - (dx_right / dx)) <= 1.0;
-            }
+            pop = true;
+        } else {
+            bool left, right;
+            edge_plane_test(cur, a, b, V, left, right);
             uint32_t left_handle, right_handle;
             cursor_children(cur, left_handle, right_handle);
-            if (left && right) {
-                stack[sp++] = left_handle;
-                cursor_descend(cur, base, right_handle);
-            } else if (left) {
-                cursor_descend(cur, base, left_handle);
-            } else if (right) {
-                cursor_descend(cur, base, right_handle);
-            } else {
-                if (sp == 0) return count;
-                cursor_enter(cur, base, stack[--sp]);
-            }
+            if (left && right) stack[sp++] = left_handle;
+            next = right ? right_handle : left_handle;
+            pop = !(left || right);
         }
-        const int4 leaf = cursor_leaf(cur);
-        for (int k = 0; k < leaf.y; k++) {
-            int bbox_index = leaf_element(leaf, t.bb_indices, k);
-            P2 c, d;
-            bool intersects;
-            if constexpr (MAXV == 0) intersects = edge_edge_intersect(t, bbox_index, a, b, c, d);
-            else intersects = edge_face_intersect<MAXV>(t, bbox_index, a, b, c, d);
-            if (intersects) {
-                emit(count, bbox_index, c, d);
-                count++;
-            }
+        if (pop) {
+            if (sp == 0) return count;
+            next = stack[--sp];
         }
-        if (sp == 0) return count;
-        cursor_enter(cur, base, stack[--sp]);
+        cursor_enter(cur, base, next);
     }
 }
 
