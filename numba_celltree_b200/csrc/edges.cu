@@ -13,9 +13,11 @@ namespace ct {
 //   * every lane walks the tree for its own segment, one node per iteration, through one branch-free step
 //     (edge_plane_test + selects), and pushes the cells of the leaves it reaches -- with their ordinal in the
 //     segment's candidate sequence -- onto a queue in shared memory that the warp shares;
-//   * whenever the queue holds 32 candidates (or the walks are over), the 32 lanes clip one candidate each, whoever
-//     pushed it; a hit is appended to the log (hitlog.cuh) with the segment, the candidate's ordinal, the cell and the
-//     clipped points, and counted for its segment.
+//   * whenever the queue holds 32 candidates (or the walks are over), the 32 lanes take one candidate each, whoever
+//     pushed it, and run the cheap half of the test (Cohen-Sutherland against the cell's box); the survivors go onto a
+//     second queue, and whenever THAT holds 32 the lanes run the expensive half (Cyrus-Beck against the polygon) on one
+//     survivor each; a hit is appended to the log (hitlog.cuh) with the segment, the candidate's ordinal, the cell and
+//     the clipped points, and counted for its segment.
 // After the scan of the counts, k_place_hits_unordered drops every hit somewhere in its segment's range, and the final
 // per-segment sort orders the range by (t, ordinal): the reference's stable sort by t of the hits in emission order
 // (geometry_utils.py:564-574), since the ordinal grows with the emission order.
@@ -30,8 +32,10 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ double2 s_segment[WARPS][32][2];
     __shared__ int32_t s_hits[WARPS][32];
-    __shared__ int32_t s_cell[WARPS][QUEUE_CAP], s_ordinal[WARPS][QUEUE_CAP];
+    __shared__ int32_t s_cell[WARPS][QUEUE_CAP], s_ordinal[WARPS][QUEUE_CAP];    // candidates
     __shared__ uint8_t s_owner[WARPS][QUEUE_CAP];
+    __shared__ int32_t s_cell2[WARPS][QUEUE_CAP], s_ordinal2[WARPS][QUEUE_CAP];  // candidates that passed the box clip
+    __shared__ uint8_t s_owner2[WARPS][QUEUE_CAP];
     const int warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31u;
     const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -61,11 +65,12 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     cursor_enter(cur, base, ROOT_HANDLE);
     int leaf_k = 0;    // cells of the current leaf already pushed
     int ordinal = 0;   // candidates of this segment pushed so far
-    int queued = 0;    // entries in the warp's queue (warp-uniform)
+    int queued = 0;    // entries in the warp's queues (warp-uniform)
+    int queued2 = 0;
     __syncwarp();
     while (true) {
         const bool walking = __any_sync(FULL, active);
-        if (!walking && queued == 0) break;
+        if (!walking && queued == 0 && queued2 == 0) break;
         // ---- one node per walking lane ------------------------------------------------------------------------------
         bool push = false;
         int cell = 0;
@@ -116,32 +121,65 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
         __syncwarp();
         // ---- 32 candidates at a time, one per lane ----------------------------------------------------------------
         const bool last = !__any_sync(FULL, active);
+        // second stage: the expensive half on (up to) 32 survivors; `flush` also takes a partial batch
+        auto clip_survivors = [&](bool flush) {
+            while (queued2 >= 32 || (flush && queued2 > 0)) {
+                const int take2 = queued2 < 32 ? queued2 : 32;
+                const int first2 = queued2 - take2;
+                const bool mine2 = (int)lane < take2;
+                const int owner2 = mine2 ? s_owner2[warp][first2 + lane] : (int)lane;
+                const int64_t owner_q = __shfl_sync(FULL, q, owner2);
+                if (mine2) {
+                    const int cell2 = s_cell2[warp][first2 + lane];
+                    const double2 a2 = s_segment[warp][owner2][0], b2 = s_segment[warp][owner2][1];
+                    P2 c, d;
+                    bool hit;
+                    if constexpr (MAXV == 0) hit = edge_edge_intersect(t, cell2, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d);
+                    else hit = edge_face_clip<MAXV>(t, cell2, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d);
+                    if (hit) {
+                        const int64_t at = hitlog_reserve(log);
+                        if (at < log.capacity) {
+                            log.q[at] = (int32_t)owner_q;
+                            log.k[at] = s_ordinal2[warp][first2 + lane];
+                            log.j[at] = cell2;
+                            double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
+                            o[0] = make_double2(c.x, c.y);
+                            o[1] = make_double2(d.x, d.y);
+                        }
+                        atomicAdd(&s_hits[warp][owner2], 1);
+                    }
+                }
+                queued2 = first2;
+                __syncwarp();
+            }
+        };
         while (queued >= 32 || (last && queued > 0)) {
             const int take = queued < 32 ? queued : 32;
             const int first = queued - take;
             const bool mine = (int)lane < take;
-            const int owner = mine ? s_owner[warp][first + lane] : (int)lane;
-            const int64_t owner_q = __shfl_sync(FULL, q, owner);
+            bool pass = false;
+            int bbox_index = 0, owner = (int)lane, ordinal_of = 0;
             if (mine) {
-                const int bbox_index = s_cell[warp][first + lane];
+                owner = s_owner[warp][first + lane];
+                bbox_index = s_cell[warp][first + lane];
+                ordinal_of = s_ordinal[warp][first + lane];
                 const double2 a2 = s_segment[warp][owner][0], b2 = s_segment[warp][owner][1];
-                P2 c, d;
-                if (edge_cell_intersect<MAXV>(t, bbox_index, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d)) {
-                    const int64_t at = hitlog_reserve(log);
-                    if (at < log.capacity) {
-                        log.q[at] = (int32_t)owner_q;
-                        log.k[at] = s_ordinal[warp][first + lane];
-                        log.j[at] = bbox_index;
-                        double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
-                        o[0] = make_double2(c.x, c.y);
-                        o[1] = make_double2(d.x, d.y);
-                    }
-                    atomicAdd(&s_hits[warp][owner], 1);
-                }
+                if constexpr (MAXV == 0) pass = true;  // segment / segment: a single test, in the second stage
+                else pass = edge_face_prefilter(t, bbox_index, P2{a2.x, a2.y}, P2{b2.x, b2.y});
             }
             queued = first;
+            const unsigned passing = __ballot_sync(FULL, pass);
+            if (pass) {
+                const int at = queued2 + __popc(passing & ((1u << lane) - 1u));
+                s_cell2[warp][at] = bbox_index;
+                s_ordinal2[warp][at] = ordinal_of;
+                s_owner2[warp][at] = (uint8_t)owner;
+            }
+            queued2 += __popc(passing);
             __syncwarp();
+            clip_survivors(false);  // keeps the second queue below 32 entries
         }
+        if (last) clip_survivors(true);  // the walks are over and the first queue is empty: flush
     }
     if (valid) counts[q] = s_hits[warp][lane];
 }

@@ -222,18 +222,26 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
 }
 
 // ---- per-candidate tests of locate_edge -------------------------------------------------------------------
-// compute_edge_face_intersect, query.py:309-328
+// compute_edge_face_intersect, query.py:309-328, in its two halves: the Cohen-Sutherland clip against the cell's
+// bounding box decides whether the cell is looked at at all (its clipped points are not used further) ...
+CT_DEV bool edge_face_prefilter(const TreeView &t, int bbox_index, P2 a, P2 b) {
+    Box4 box = load_box(t.bb_coords, bbox_index);
+    P2 c, d;
+    return cohen_sutherland_line_box_clip(a, b, box, c, d) != 0;
+}
+// ... and the Cyrus-Beck clip against the cell's polygon gives the intersection
+template <int MAXV>
+CT_DEV bool edge_face_clip(const TreeView &t, int bbox_index, P2 a, P2 b, P2 &c, P2 &d) {
+    Box4 box = load_box(t.bb_coords, bbox_index);
+    Poly<MAXV> polygon;
+    load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, polygon);
+    double tolerance = nb_max(MIN_TOLERANCE, TOLERANCE_FACTOR * nb_max(box.xmax - box.xmin, box.ymax - box.ymin));
+    return cyrus_beck_line_polygon_clip<MAXV>(a, b, polygon, tolerance, c, d);
+}
 template <int MAXV>
 CT_DEV bool edge_face_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P2 &c, P2 &d) {
-    Box4 box = load_box(t.bb_coords, bbox_index);
-    bool intersects = cohen_sutherland_line_box_clip(a, b, box, c, d) != 0;
-    if (intersects) {
-        Poly<MAXV> polygon;
-        load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, polygon);
-        double tolerance = nb_max(MIN_TOLERANCE, TOLERANCE_FACTOR * nb_max(box.xmax - box.xmin, box.ymax - box.ymin));
-        intersects = cyrus_beck_line_polygon_clip<MAXV>(a, b, polygon, tolerance, c, d);
-    }
-    return intersects;
+    if (!edge_face_prefilter(t, bbox_index, a, b)) return false;
+    return edge_face_clip<MAXV>(t, bbox_index, a, b, c, d);
 }
 
 // compute_edge_edge_intersect, query.py:292-306

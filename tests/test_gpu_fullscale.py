@@ -9,7 +9,8 @@ import hashlib
 import numpy as np
 import pytest
 
-from numba_celltree_b200.synthetic import c2_points, delaunay_mesh, quad_mesh
+import oracle
+from numba_celltree_b200.synthetic import c2_points, c3_boxes, c4_edges, delaunay_mesh, quad_mesh
 
 pytestmark = pytest.mark.gpu
 
@@ -62,3 +63,38 @@ def test_c3_tree_matches_reference_fingerprints(pkg):
     assert len(i) == 7_348_217
     assert abs(area.sum() - 0.999965944659) < 1e-11
     assert np.all(np.diff(i) >= 0)
+
+
+def test_c3_boxes_and_c4_edges_at_full_size(pkg):
+    """10 M boxes / 10 M segments against the 2 M-triangle tree: totals, ordering, and the first 150 000 queries'
+    pairs (which do not depend on the rest of the batch) bit for bit against the oracle."""
+    vertices, faces = delaunay_mesh(1_000_000, seed=1234)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    head = 150_000
+
+    boxes = c3_boxes(len(faces), 10_000_000)
+    i, j, area = tree.intersect_boxes(boxes)
+    assert len(i) == 111_246_104 and np.all(np.diff(i) >= 0) and (area > 0).all()
+    ri, rj, ra = ref.intersect_boxes(boxes[:head])
+    k = np.searchsorted(i, head)
+    assert np.array_equal(i[:k], ri) and np.array_equal(j[:k], rj) and np.array_equal(area[:k], ra)
+    del i, j, area
+    i, j = tree.locate_boxes(boxes)
+    assert len(i) == 126_457_665 and np.all(np.diff(i) >= 0)
+    ri, rj = ref.locate_boxes(boxes[:head])
+    k = np.searchsorted(i, head)
+    assert np.array_equal(i[:k], ri) and np.array_equal(j[:k], rj)
+    del i, j, boxes
+
+    edges = c4_edges(len(faces), 10_000_000)
+    i, j, xy = tree.intersect_edges(edges)
+    assert len(i) == 86_544_887 and np.all(np.diff(i) >= 0)
+    ri, rj, rxy = ref.intersect_edges(edges[:head])
+    k = np.searchsorted(i, head)
+    assert np.array_equal(i[:k], ri) and np.array_equal(j[:k], rj) and np.array_equal(xy[:k], rxy, equal_nan=True)
+    # along every segment the pieces come in order of t = (c - a) . (b - a) (sort_intersections_by_edge)
+    a, b = edges[i, 0], edges[i, 1]
+    t = ((xy[:, 0] - a) * (b - a)).sum(axis=1)
+    same = i[1:] == i[:-1]
+    assert not np.any(same & (t[1:] < t[:-1]))
