@@ -8,7 +8,10 @@ namespace ct {
 // Queries per thread.  A thread's queries are gathered together up front: their indices (coalesced reads of `perm`),
 // then their points as asynchronous 16-byte copies into shared memory that are all in flight at once -- the two
 // dependent DRAM round trips (index, then point) are paid once per PER_THREAD queries instead of once per query.
-constexpr int PER_THREAD = 4;
+#ifndef CT_POINTS_PER_THREAD
+#define CT_POINTS_PER_THREAD 4
+#endif
+constexpr int PER_THREAD = CT_POINTS_PER_THREAD;
 
 CT_DEV void async_copy_16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
