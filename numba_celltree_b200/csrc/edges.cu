@@ -1,5 +1,6 @@
-// edges.cu -- ct_intersect_edges: count -> scan -> fill traversal of query segments (Cohen-Sutherland +
-// Cyrus-Beck against faces, segment/segment against a network), then the per-edge stable sort by t.
+// edges.cu -- ct_intersect_edges: warp-cooperative traversal of the query segments that counts and logs the hits
+// (Cohen-Sutherland + Cyrus-Beck against faces, segment/segment against a network), scan, placement, and the
+// per-segment sort by (t, emission ordinal).
 #include "hitlog.cuh"
 #include "morton.cuh"
 #include "traverse.cuh"

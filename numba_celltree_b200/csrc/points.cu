@@ -1,5 +1,6 @@
-// points.cu -- ct_locate_points: Morton ordering of the queries, one-thread-per-point traversal with the
-// point-in-polygon test and fused barycentric weights at the hit.
+// points.cu -- ct_locate_points: Morton ordering of the queries, the traversal kernel (entry grid, treelet descent,
+// point-in-polygon test, fused barycentric weights at the hit; four points per thread), results written in execution
+// order and un-permuted through one radix pass; for host buffers a chunked three-stream pipeline around it.
 #include "morton.cuh"
 #include "traverse.cuh"
 
@@ -8,10 +9,7 @@ namespace ct {
 // Queries per thread.  A thread's queries are gathered together up front: their indices (coalesced reads of `perm`),
 // then their points as asynchronous 16-byte copies into shared memory that are all in flight at once -- the two
 // dependent DRAM round trips (index, then point) are paid once per PER_THREAD queries instead of once per query.
-#ifndef CT_POINTS_PER_THREAD
-#define CT_POINTS_PER_THREAD 4
-#endif
-constexpr int PER_THREAD = CT_POINTS_PER_THREAD;
+constexpr int PER_THREAD = 4;  // measured on C2, traversal ms per 100 M points: 2 -> 3.97, 4 -> 3.79, 8 -> 3.84
 
 CT_DEV void async_copy_16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)

@@ -1,15 +1,20 @@
-// traverse.cuh -- per-query stack traversal of the cell tree (one thread per query).
+// traverse.cuh -- per-query stack traversal of the cell tree.
 //
 // The reference keeps an explicit stack of node indices (query.py:63-107, 177-244, 357-455), pushes
-// child A then child B and pops B first.  Here the node to visit next lives in a register and only the
-// deferred sibling goes to the per-thread stack: "push A, push B" becomes "stack <- A, next = B".
+// child A then child B and pops B first.  Here a Cursor sits on the node to visit next and only the
+// deferred sibling goes to the per-thread stack: "push A, push B" becomes "stack <- A, cursor -> B".
 // The visiting order -- and with it the first-hit result of locate_points and the emission order of
-// box / edge pairs -- is exactly the reference's.
+// box / edge pairs -- is exactly the reference's.  The nodes are read through the treelets of common.cuh
+// (three levels per 128-byte line); a stack entry is a node handle (treelet << 3 | slot).
 //
 // The stack is a per-thread local array: it is thread-interleaved in local memory, so the 32 lanes of a
 // warp touch one 128-byte line per slot, and it stays in L1.  Live depth is at most (tree depth - 1):
 // one deferred sibling per level of the current path.  ct_tree.depth is checked against STACK_CAP before
 // any launch (CT_ERR_DEPTH instead of silent truncation).
+//
+// Points walk in two nested loops (descend; then the leaf), their lanes move in step.  Boxes and segments walk
+// in one loop whose step has as few divergent paths as possible (the outcome of an inner node becomes selects and
+// a predicated push): their lanes are at different kinds of node most of the time.
 #pragma once
 
 #include "geometry.cuh"
@@ -17,8 +22,6 @@
 namespace ct {
 
 constexpr int STACK_CAP = 64;
-
-constexpr int LEAF_INLINE = 2;  // element ids stored with a leaf position of a treelet
 
 // ---- the descent, shared by the four traversals ---------------------------------------------------------------
 // Cursor on one binary node = (treelet, slot), see common.cuh.  The node's 16-byte slot is loaded when the cursor
