@@ -82,7 +82,7 @@ CT_DEV int4 cursor_leaf(const Cursor &c) {  // {ptr, size, id0, id1}
     const long long a = __double_as_longlong(c.plane.x), b = __double_as_longlong(c.plane.y);
     return make_int4((int)(a & 0xffffffffLL), (int)(a >> 32), (int)(b & 0xffffffffLL), (int)(b >> 32));
 }
-// k-th element of a leaf: the first LEAF_INLINE ids travel with the node, the rest come from bb_indices
+// k-th element of a leaf: the first two ids travel with the node, the rest come from bb_indices
 CT_DEV int leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices, int k) {
     return k == 0 ? leaf.z : (k == 1 ? leaf.w : __ldg(bb_indices + leaf.x + k));
 }
