@@ -2,7 +2,16 @@
 
 __version__ = "0.1.0"
 
-__all__ = ("CellTree2d", "EdgeCellTree2d")
+__all__ = ("CellTree2d", "EdgeCellTree2d", "trim_memory")
+
+
+def trim_memory() -> None:
+    """Give the library's cached device blocks and page-locked host blocks back to the driver."""
+    from numba_celltree_b200 import _lib
+
+    lib = _lib.load()
+    lib.ct_device_trim()
+    lib.ct_host_trim()
 
 
 def __getattr__(name):

@@ -71,3 +71,18 @@ def test_argument_validation_happens_before_the_device_is_touched():
         CellTree2d(v, np.zeros((1, 33), dtype=int), -1)
     with pytest.raises(ValueError):
         EdgeCellTree2d(v, [[0, 1]], n_buckets=1)
+
+
+def test_result_arrays_fall_back_to_pageable_memory_when_pinning_is_refused():
+    """Without a CUDA device page-locking fails: results are then plain ndarrays (memory only -- compute has no fallback)."""
+    import torch
+
+    from numba_celltree_b200 import _lib
+
+    a = _lib.result_array((1 << 18,), np.int64)  # 2 MiB: above the pinning threshold
+    assert a.shape == (1 << 18,) and a.dtype == np.int64 and a.flags.writeable and a.flags.c_contiguous
+    a[:] = 7
+    b = _lib.result_array((3, 5), np.float64)  # small: always plain
+    assert b.flags.owndata and b.shape == (3, 5)
+    if not torch.cuda.is_available():
+        assert a.flags.owndata
