@@ -1128,14 +1128,14 @@ static int upload_mesh(ct_tree *tree, const double *vertices, const int64_t *ele
     CT_CHECK(dalloc(&tree->vertices, (size_t)(nv > 0 ? nv : 1), s));
     CT_CHECK(dalloc(&tree->elements, (size_t)(ne * M > 0 ? ne * M : 1), s));
     CT_CHECK(dalloc(&tree->bb_coords, 4 * (size_t)(ne > 0 ? ne : 1), s));
-    cudaMemcpyKind kind = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CT_CUDA(cudaMemcpyAsync(tree->vertices, vertices, sizeof(double2) * (size_t)nv, kind, s));
     if (mem == CT_MEM_DEVICE) {
+        CT_CUDA(cudaMemcpyAsync(tree->vertices, vertices, sizeof(double2) * (size_t)nv, cudaMemcpyDeviceToDevice, s));
         CT_CHECK(launch_narrow(elements, ne * M, tree->elements, s));
     } else {
+        CT_CHECK(upload_from_host(tree->vertices, vertices, sizeof(double2) * (size_t)nv, s));
         Scratch<int64_t> tmp;
         CT_CHECK(tmp.alloc((size_t)ne * M, s));
-        CT_CUDA(cudaMemcpyAsync(tmp.p, elements, sizeof(int64_t) * (size_t)ne * M, cudaMemcpyHostToDevice, s));
+        CT_CHECK(upload_from_host(tmp.p, elements, sizeof(int64_t) * (size_t)ne * M, s));
         CT_CHECK(launch_narrow(tmp.p, ne * M, tree->elements, s));
         CT_CUDA(cudaStreamSynchronize(s));
     }
@@ -1259,8 +1259,12 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
     tree->n_nodes = n_nodes;
     auto body = [&]() -> int {
         CT_CHECK(upload_mesh(tree, vertices, elements, mem, s));
-        cudaMemcpyKind kind_cp = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        CT_CUDA(cudaMemcpyAsync(tree->bb_coords, bb_coords, sizeof(double) * 4 * (size_t)n_elem, kind_cp, s));
+        auto copy_in = [&](void *dst, const void *src, size_t bytes) -> int {
+            if (mem != CT_MEM_DEVICE) return upload_from_host(dst, src, bytes, s);
+            CT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+            return CT_OK;
+        };
+        CT_CHECK(copy_in(tree->bb_coords, bb_coords, sizeof(double) * 4 * (size_t)n_elem));
         CT_CHECK(dalloc(&tree->bb_indices, (size_t)n_elem, s));
         CT_CHECK(dalloc(&tree->nodes, (size_t)n_nodes, s));
         {
@@ -1268,14 +1272,14 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
             const int64_t *src = bb_indices;
             if (mem != CT_MEM_DEVICE) {
                 CT_CHECK(tmp.alloc(n_elem, s));
-                CT_CUDA(cudaMemcpyAsync(tmp.p, bb_indices, sizeof(int64_t) * (size_t)n_elem, cudaMemcpyHostToDevice, s));
+                CT_CHECK(upload_from_host(tmp.p, bb_indices, sizeof(int64_t) * (size_t)n_elem, s));
                 src = tmp.p;
             }
             CT_CHECK(launch_narrow(src, n_elem, tree->bb_indices, s));
             Scratch<unsigned char> packed;
             size_t bytes = (size_t)n_nodes * NODE41;
             CT_CHECK(packed.alloc(bytes + 4, s));
-            CT_CUDA(cudaMemcpyAsync(packed.p, nodes, bytes, kind_cp, s));
+            CT_CHECK(copy_in(packed.p, nodes, bytes));
             k_unpack_nodes<<<grid_for(n_nodes, BB), BB, 0, s>>>(packed.p, n_nodes, tree->nodes);
             CT_LAUNCH_CHECK();
             Scratch<int32_t> parent, max_depth;

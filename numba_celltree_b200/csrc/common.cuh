@@ -140,6 +140,12 @@ inline void dfree(void *p, cudaStream_t s) {
     if (p) pool_free(p, s);
 }
 
+// Host -> device copy of a caller's array.  Pageable memory (a plain ndarray) goes through the driver's staging at
+// ~10 GB/s; large arrays are therefore copied by a few host threads into two page-locked staging blocks that the copy
+// engine drains at the PCIe rate while the threads fill the other one.  Page-locked sources are copied directly.
+// The call returns when the source has been consumed (the device copy itself is ordered on `s`).
+int upload_from_host(void *dst_device, const void *src_host, size_t bytes, cudaStream_t s);
+
 // Owns a stream-ordered allocation for the duration of a call.
 template <typename T>
 struct Scratch {
@@ -190,7 +196,7 @@ struct DevIn {
             return CT_OK;
         }
         CT_CHECK(owned.alloc(count, s));
-        if (count) CT_CUDA(cudaMemcpyAsync(owned.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (count) CT_CHECK(upload_from_host(owned.p, src, count * sizeof(T), s));
         p = owned.p;
         return CT_OK;
     }

@@ -6,6 +6,9 @@
 #include <ctime>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <cstring>
 #include <unordered_map>
 
 #include "traverse.cuh"
@@ -391,6 +394,72 @@ extern "C" void ct_host_trim(void) {
     }
     for (auto &kv : blocks) cudaFreeHost(kv.second);
 }
+
+namespace ct {
+int upload_from_host(void *dst_device, const void *src_host, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return CT_OK;
+    constexpr size_t STAGED_FROM = (size_t)8 << 20;  // below this the plain copy is as good
+    constexpr size_t BLOCK_BYTES = (size_t)32 << 20;
+    bool pageable = true;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src_host) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    static int n_threads = -1;
+    if (n_threads < 0) {
+        const char *e = getenv("CELLTREE_COPY_THREADS");
+        int hw = (int)std::thread::hardware_concurrency();
+        n_threads = e ? atoi(e) : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));  // measured on the pool's 16-core hosts: 4 copies as fast as 8
+        if (n_threads < 1) n_threads = 1;
+    }
+    if (!pageable || bytes < STAGED_FROM || n_threads == 1) {
+        CT_CUDA(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, s));
+        if (pageable) CT_CUDA(cudaStreamSynchronize(s));  // the driver may still be reading a pageable source
+        return CT_OK;
+    }
+    void *stage[2] = {nullptr, nullptr};
+    cudaEvent_t drained[2] = {nullptr, nullptr};
+    int status = CT_OK;
+    auto body = [&]() -> int {
+        for (int k = 0; k < 2; k++) {
+            CT_CHECK(ct_host_alloc(BLOCK_BYTES, &stage[k]));
+            CT_CUDA(cudaEventCreateWithFlags(&drained[k], cudaEventDisableTiming));
+        }
+        const char *src = static_cast<const char *>(src_host);
+        char *dst = static_cast<char *>(dst_device);
+        int k = 0;
+        bool used[2] = {false, false};
+        for (size_t off = 0; off < bytes; off += BLOCK_BYTES, k ^= 1) {
+            const size_t len = bytes - off < BLOCK_BYTES ? bytes - off : BLOCK_BYTES;
+            if (used[k]) CT_CUDA(cudaEventSynchronize(drained[k]));  // the copy engine is done with this block
+            const size_t slice = (len + n_threads - 1) / n_threads;
+            std::vector<std::thread> workers;
+            for (int t = 1; t < n_threads; t++) {
+                const size_t lo = (size_t)t * slice;
+                if (lo >= len) break;
+                const size_t n = len - lo < slice ? len - lo : slice;
+                workers.emplace_back([=]() { memcpy(static_cast<char *>(stage[k]) + lo, src + off + lo, n); });
+            }
+            memcpy(stage[k], src + off, len < slice ? len : slice);
+            for (auto &w : workers) w.join();
+            CT_CUDA(cudaMemcpyAsync(dst + off, stage[k], len, cudaMemcpyHostToDevice, s));
+            CT_CUDA(cudaEventRecord(drained[k], s));
+            used[k] = true;
+        }
+        for (int q = 0; q < 2; q++)
+            if (used[q]) CT_CUDA(cudaEventSynchronize(drained[q]));
+        return CT_OK;
+    };
+    status = body();
+    for (int k = 0; k < 2; k++) {
+        if (status != CT_OK && drained[k]) cudaEventSynchronize(drained[k]);
+        if (drained[k]) cudaEventDestroy(drained[k]);
+        ct_host_free(stage[k]);
+    }
+    return status;
+}
+}  // namespace ct
 
 extern "C" const char *ct_last_error(void) { return g_error.c_str(); }
 

@@ -194,7 +194,7 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         int k = 0;
         for (int64_t lo = 0; lo < n; lo += chunk, k = (k + 1) % NS) {
             int64_t m = (n - lo) < chunk ? (n - lo) : chunk;
-            CT_CUDA(cudaMemcpyAsync(d_pts[k], points + 2 * lo, m * sizeof(double2), cudaMemcpyHostToDevice, st[k]));
+            CT_CHECK(upload_from_host(d_pts[k], points + 2 * lo, m * sizeof(double2), st[k]));
             CT_CHECK(locate_points_device(tree, d_pts[k], m, tolerance, d_out[k], weights ? d_w[k] : nullptr, st[k]));
             CT_CUDA(cudaMemcpyAsync(out_index + lo, d_out[k], m * sizeof(int64_t), cudaMemcpyDeviceToHost, st[k]));
             if (weights)
