@@ -92,9 +92,6 @@ CT_DEV int leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices
 // Two nested loops: the inner one only descends (a handful of registers), the outer one tests the cells of the
 // leaf it arrived at (query.py:72-85) -- so that the register allocation of the descent is not weighed down by
 // the point-in-polygon test.
-#ifndef CT_POINT_LOOPS
-#define CT_POINT_LOOPS 2
-#endif
 template <int MAXV>
 CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
     uint32_t stack[STACK_CAP];
@@ -102,39 +99,6 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
     cursor_enter(c, base, entry_handle(t.entry, p));
-#if CT_POINT_LOOPS == 1
-    while (true) {
-        uint32_t next = 0;
-        bool pop;
-        if (cursor_is_leaf(c)) {
-            const int4 leaf = cursor_leaf(c);
-            for (int k = 0; k < leaf.y; k++) {
-                int bbox_index = leaf_element(leaf, t.bb_indices, k);
-                Poly<MAXV> poly;
-                load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, poly);
-                if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
-            }
-            pop = true;
-        } else {
-            const double Lmax = c.plane.x, Rmin = c.plane.y;
-            const double pd = cursor_dim(c) ? p.y : p.x;
-            const bool left = pd <= Lmax;
-            const bool right = pd >= Rmin;
-            uint32_t left_handle, right_handle;
-            cursor_children(c, left_handle, right_handle);
-            // nearer-plane heuristic, query.py:93-101: the child pushed LAST is visited first
-            const bool right_first = (left && right) ? ((Lmax - pd) < (pd - Rmin)) : right;
-            if (left && right) stack[sp++] = right_first ? left_handle : right_handle;
-            next = right_first ? right_handle : left_handle;
-            pop = !(left || right);
-        }
-        if (pop) {
-            if (sp == 0) return -1;
-            next = stack[--sp];
-        }
-        cursor_enter(c, base, next);
-    }
-#else
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;
@@ -167,7 +131,6 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
         if (sp == 0) return -1;
         cursor_enter(c, base, stack[--sp]);
     }
-#endif
 }
 
 // ---- locate_point_on_edge, query.py:121-165 ---------------------------------------------------------------
