@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.device_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
         except OSError:
@@ -283,12 +283,14 @@ def main():
         return float(t.item())
 
     # ---- device-resident steps ---------------------------------------------------------------------------------
+    # clocks / throttle reasons are sampled from the warm-up on, through the device-resident steps, the per-kernel steps
+    # and the end-to-end steps (the device-resident region alone lasts under 0.1 s: too short for more than a sample)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     dev_out = None
     for _ in range(args.warmup):
         dev_out = tree.locate_points(dev_points)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.ct_launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -297,7 +299,6 @@ def main():
     stop.record()
     barrier()
     launches = lib.ct_launch_count() - launches0
-    clocks = sampler.stop()
     ms_total = max_over_ranks(start.elapsed_time(stop))
     ms_per_step = ms_total / args.steps
     value = world * n_points / (ms_per_step * 1e-3)
@@ -384,6 +385,7 @@ def main():
         tree.locate_points(host_np, out=out_np)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
     e2e = {
         "value": world * n_points * args.steps / e2e_s,
         "unit": UNIT,
