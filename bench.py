@@ -129,6 +129,27 @@ class ClockSampler:
         }
 
 
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """Only the result line may go to stdout: libraries that print there (NCCL's version banner) are sent to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -202,7 +223,7 @@ def run_reference(args):
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -214,6 +235,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -453,7 +475,7 @@ def main():
             "secondary": secondary,
             "barycentric_weights": weights_line,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
