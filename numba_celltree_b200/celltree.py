@@ -118,22 +118,43 @@ class CellTree2d(CellTree2dBase):
         """Pairs (box index, face index) with a positive area of intersection, and that area."""
         return self._boxes(bbox_coords, with_area=True)
 
-    def _faces(self, vertices, faces, fill_value: int, write_back: bool, with_area: bool):
+    def _faces(self, vertices, faces, fill_value: int, write_back: bool, with_area: bool, device=None):
         handle = ctypes.c_void_p()
         _lib.check(
             _lib.load().ct_locate_faces(
-                self._tree.handle, vertices.ctypes.data, vertices.shape[0], faces.ctypes.data, faces.shape[0],
-                faces.shape[1], int(fill_value), int(write_back), int(with_area), _lib.CT_MEM_HOST, ctypes.byref(handle),
+                self._tree.handle, _ptr(vertices), vertices.shape[0], _ptr(faces), faces.shape[0],
+                faces.shape[1], int(fill_value), int(write_back), int(with_area),
+                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
             )
         )  # fmt: skip
-        return self._fetch(handle, payload_shape=())
+        return self._fetch(handle, payload_shape=(), device=device)
+
+    @staticmethod
+    def _device_mesh(vertices, faces):
+        """A query mesh given as CUDA tensors (float64 ``(n, 2)``, int64 ``(n_face, n_max_vert)``): checked, contiguous."""
+        if not (_is_cuda_tensor(vertices) and _is_cuda_tensor(faces)):
+            raise ValueError("vertices and faces must both be CUDA tensors or both be host arrays")
+        if vertices.dim() != 2 or vertices.shape[1] != 2 or str(vertices.dtype) != "torch.float64":
+            raise ValueError("vertices must have shape (n_points, 2)")
+        if str(faces.dtype) != "torch.int64":
+            raise ValueError("faces must be an int64 tensor of shape (n_face, n_max_vert)")
+        check_faces_shape(faces)
+        if vertices.device != faces.device:
+            raise ValueError("vertices and faces must be on the same device")
+        return vertices.contiguous(), faces.contiguous()
 
     def locate_faces(self, vertices: FloatArray, faces: IntArray) -> Tuple[IntArray, IntArray]:
         """
         Pairs (face index, tree face index) that overlap according to the separating axis theorem.
         As in the reference (celltree.py:212) ``faces`` is made counter-clockwise IN PLACE when it is a
-        contiguous intp array.
+        contiguous intp array (or a contiguous int64 CUDA tensor; results are then CUDA tensors).
         """
+        if _is_cuda_tensor(vertices) or _is_cuda_tensor(faces):
+            vertices_c, faces_c = self._device_mesh(vertices, faces)
+            i, j, _ = self._faces(vertices_c, faces_c, -1, write_back=True, with_area=False, device=faces_c.device)
+            if faces_c is not faces:
+                faces.copy_(faces_c)
+            return i, j
         vertices_c = np.ascontiguousarray(vertices, dtype=np.float64)
         faces_c = np.ascontiguousarray(faces, dtype=IntDType)
         if vertices_c.ndim != 2 or vertices_c.shape[1] != 2:
@@ -148,7 +169,12 @@ class CellTree2d(CellTree2dBase):
     def intersect_faces(
         self, vertices: FloatArray, faces: IntArray, fill_value: int
     ) -> Tuple[IntArray, IntArray, FloatArray]:
-        """Pairs (face index, tree face index) with a positive area of intersection, and that area."""
+        """Pairs (face index, tree face index) with a positive area of intersection, and that area.
+        With CUDA tensors as the query mesh the three results are CUDA tensors: the (i, j, area) triplets of the
+        regridding weights stay on the device."""
+        if _is_cuda_tensor(vertices) or _is_cuda_tensor(faces):
+            vertices, faces = self._device_mesh(vertices, faces)
+            return self._faces(vertices, faces, fill_value, write_back=False, with_area=True, device=faces.device)
         vertices = cast_vertices(vertices)
         if isinstance(faces, np.ndarray) and faces.dtype == IntDType and faces.flags.c_contiguous:
             # cast_faces' checks without its copy: the device works on its own copy of the faces and treats

@@ -175,6 +175,12 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         CHUNK = e ? atoll(e) : (1 << 22);
         if (CHUNK < 1024) CHUNK = 1024;
     }
+    static int64_t TAIL_MIN = -1;  // smallest chunk of the ramp-down at the end of a batch; 0 = uniform chunks
+    if (TAIL_MIN < 0) {
+        const char *e = getenv("CELLTREE_HOST_TAIL");
+        TAIL_MIN = e ? atoll(e) : (1 << 18);
+        if (TAIL_MIN < 0) TAIL_MIN = 0;
+    }
     constexpr int NS = 3;
     const int M = tree->M;
     cudaStream_t st[NS];
@@ -192,8 +198,17 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
             if (weights) CT_CHECK(dalloc(&d_w[k], chunk * M, st[k]));
         }
         int k = 0;
-        for (int64_t lo = 0; lo < n; lo += chunk, k = (k + 1) % NS) {
-            int64_t m = (n - lo) < chunk ? (n - lo) : chunk;
+        int64_t m = 0;
+        for (int64_t lo = 0; lo < n; lo += m, k = (k + 1) % NS) {
+            // The host-to-device copy engine is the bottleneck and runs without a gap, so the call ends one chunk's
+            // kernels + result copy after the last input byte has arrived: the last chunks are halved down to TAIL_MIN
+            // so that this drain is short (full-size chunks everywhere else keep the per-chunk launch cost low).
+            const int64_t rest = n - lo;
+            m = rest < chunk ? rest : chunk;
+            if (TAIL_MIN > 0 && n > chunk && rest < 2 * chunk && rest > TAIL_MIN) {
+                m = rest / 2 > TAIL_MIN ? rest / 2 : TAIL_MIN;
+                if (m > chunk) m = chunk;
+            }
             CT_CHECK(upload_from_host(d_pts[k], points + 2 * lo, m * sizeof(double2), st[k]));
             CT_CHECK(locate_points_device(tree, d_pts[k], m, tolerance, d_out[k], weights ? d_w[k] : nullptr, st[k]));
             CT_CUDA(cudaMemcpyAsync(out_index + lo, d_out[k], m * sizeof(int64_t), cudaMemcpyDeviceToHost, st[k]));

@@ -138,6 +138,32 @@ def test_device_resident_inputs_match_host(delaunay_pair):
     assert np.array_equal(dxy.cpu().numpy(), xy, equal_nan=True)
 
 
+def test_device_resident_query_mesh_matches_host(delaunay_pair):
+    """intersect_faces / locate_faces with the query mesh as CUDA tensors: same pairs and areas, results on the device,
+    and locate_faces turns clockwise query faces counter-clockwise in place (celltree.py:212) on the device too."""
+    torch = pytest.importorskip("torch")
+    tree, ref, _, _ = delaunay_pair
+    qv, qf = quad_mesh(150, 120)
+    qf = qf.copy()
+    qf[::3] = qf[::3, ::-1]  # every third face clockwise
+    ri, rj, ra = ref.intersect_faces(qv, qf, -1)
+    dqv, dqf = torch.from_numpy(qv).cuda(), torch.from_numpy(qf).cuda()
+    di, dj, da = tree.intersect_faces(dqv, dqf, -1)
+    assert di.is_cuda and dj.is_cuda and da.is_cuda
+    assert np.array_equal(di.cpu().numpy(), ri) and np.array_equal(dj.cpu().numpy(), rj)
+    np.testing.assert_allclose(da.cpu().numpy(), ra, rtol=RTOL, atol=0)
+    assert np.array_equal(dqf.cpu().numpy(), qf), "intersect_faces must not modify the caller's faces"
+    host_faces = qf.copy()
+    hi, hj = tree.locate_faces(qv, host_faces)
+    li, lj = tree.locate_faces(dqv, dqf)
+    assert np.array_equal(li.cpu().numpy(), hi) and np.array_equal(lj.cpu().numpy(), hj)
+    assert np.array_equal(dqf.cpu().numpy(), host_faces), "locate_faces makes the faces counter-clockwise in place"
+    with pytest.raises(ValueError):
+        tree.intersect_faces(dqv, qf, -1)  # mixed host / device mesh
+    with pytest.raises(ValueError):
+        tree.intersect_faces(dqv, dqf.to(torch.int32), -1)
+
+
 def test_boxes(delaunay_pair):
     tree, ref, _, faces = delaunay_pair
     boxes = c3_boxes(len(faces), 300_000)
