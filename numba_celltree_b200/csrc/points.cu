@@ -178,7 +178,7 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
     static int64_t TAIL_MIN = -1;  // smallest chunk of the ramp-down at the end of a batch; 0 = uniform chunks
     if (TAIL_MIN < 0) {
         const char *e = getenv("CELLTREE_HOST_TAIL");
-        TAIL_MIN = e ? atoll(e) : (1 << 18);
+        TAIL_MIN = e ? atoll(e) : (1 << 16);  // measured on C2: 32.76 ms uniform, 32.47 with 2^18, 32.35 with 2^16
         if (TAIL_MIN < 0) TAIL_MIN = 0;
     }
     constexpr int NS = 3;

@@ -7,8 +7,8 @@ no collective, and variable-length results need exactly one all-gather of the pe
 local offsets into global offsets.  Concatenating the per-rank results in rank order reproduces the
 single-GPU (= the reference's) output order.
 
-The host-side logic (shard_range, exchange_totals) is backend-agnostic and is exercised with gloo on CPU in
-tests/test_distributed.py.
+The host-side logic (shard_range, exchange_totals, the *_sharded calls, gather_pairs) is backend-agnostic and is
+exercised with gloo on CPU in tests/test_distributed.py.
 """
 
 from __future__ import annotations
@@ -46,6 +46,93 @@ def exchange_totals(local_total: int, device=None):
 def globalize_pairs(i_local, lo: int):
     """Local query indices of a shard -> global query indices (the shard starts at query `lo`)."""
     return i_local + lo
+
+
+def _rows(queries, lo: int, hi: int):
+    """Rows [lo, hi) of a query array (ndarray, CUDA tensor or anything sliceable); lists are converted first."""
+    if not hasattr(queries, "shape"):
+        queries = np.asarray(queries)
+    return queries[lo:hi]
+
+
+def locate_points_sharded(tree, points, tolerance=None, weights: bool = False):
+    """
+    This rank's share of ``tree.locate_points(points)`` (or ``compute_barycentric_weights`` with ``weights=True``):
+    every rank passes the SAME `points` (or at least an array of the same length whose rows [lo, hi) are valid) and
+    gets ``(lo, hi, result)`` for its contiguous range.  Fixed-size results need no collective: writing each
+    rank's result to rows [lo, hi) of one array reproduces the single-GPU output.
+    """
+    import torch.distributed as dist
+
+    lo, hi = shard_range(len(points), dist.get_rank(), dist.get_world_size())
+    mine = _rows(points, lo, hi)
+    result = tree.compute_barycentric_weights(mine, tolerance) if weights else tree.locate_points(mine, tolerance)
+    return lo, hi, result
+
+
+def query_pairs_sharded(tree, method: str, queries, *args, device=None):
+    """
+    This rank's share of a variable-length query -- `method` is one of ``locate_boxes``, ``intersect_boxes``,
+    ``intersect_edges`` (queries = boxes / segments) -- over the contiguous range of `queries` this rank owns.
+    Returns ``(i_global, j, payload_or_None, offset, total)``: the local pairs with GLOBAL query indices, the position
+    of this rank's first pair in the concatenated (= single-GPU = reference) result and the grand total, obtained with
+    the path's one collective (an all-gather of the per-rank pair counts).
+    """
+    import torch.distributed as dist
+
+    if method not in ("locate_boxes", "intersect_boxes", "intersect_edges"):
+        raise ValueError(f"query_pairs_sharded: unsupported method {method!r}")
+    lo, hi = shard_range(len(queries), dist.get_rank(), dist.get_world_size())
+    out = getattr(tree, method)(_rows(queries, lo, hi), *args)
+    i_local, j = out[0], out[1]
+    payload = out[2] if len(out) > 2 else None
+    offset, total, _ = exchange_totals(len(i_local), device=device)
+    return globalize_pairs(i_local, lo), j, payload, offset, total
+
+
+def intersect_faces_sharded(tree, vertices, faces, fill_value: int, device=None):
+    """
+    This rank's share of ``tree.intersect_faces(vertices, faces, fill_value)``: the query FACES are split into contiguous
+    ranges (every rank holds the whole vertex array, which its faces index into); same return value as
+    `query_pairs_sharded`.  Regridding: each rank ends up with the weight triplets of its own target cells.
+    """
+    import torch.distributed as dist
+
+    lo, hi = shard_range(len(faces), dist.get_rank(), dist.get_world_size())
+    i_local, j, area = tree.intersect_faces(vertices, _rows(faces, lo, hi), fill_value)
+    offset, total, _ = exchange_totals(len(i_local), device=device)
+    return globalize_pairs(i_local, lo), j, area, offset, total
+
+
+def gather_pairs(i_global, j, payload, offset: int, total: int, dst: int = 0):
+    """
+    Assemble the sharded pairs on rank `dst` as host arrays in the reference's order (other ranks get None).
+    The ranks' pieces are variable-length, so this is an object gather of NumPy arrays: meant for results that must
+    end up on one host anyway; device-resident consumers keep their shard and use `offset`.
+    """
+    import torch.distributed as dist
+
+    def host(a):
+        if a is None or isinstance(a, np.ndarray):
+            return a
+        return a.detach().cpu().numpy()
+
+    piece = (int(offset), host(i_global), host(j), host(payload))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pieces = [None] * world if rank == dst else None
+    dist.gather_object(piece, pieces, dst=dst)
+    if rank != dst:
+        return None
+    i_all = np.empty(total, dtype=np.intp)
+    j_all = np.empty(total, dtype=np.intp)
+    first_payload = next((p[3] for p in pieces if p[3] is not None), None)
+    p_all = None if first_payload is None else np.empty((total,) + first_payload.shape[1:], dtype=np.float64)
+    for off, pi, pj, pp in pieces:
+        i_all[off : off + len(pi)] = pi
+        j_all[off : off + len(pj)] = pj
+        if p_all is not None:
+            p_all[off : off + len(pi)] = pp
+    return i_all, j_all, p_all
 
 
 def export_device_arrays(tree, device):

@@ -9,7 +9,14 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from numba_celltree_b200.distributed import exchange_totals, globalize_pairs, shard_range
+from numba_celltree_b200.distributed import (
+    exchange_totals,
+    gather_pairs,
+    globalize_pairs,
+    locate_points_sharded,
+    query_pairs_sharded,
+    shard_range,
+)
 
 
 def test_shard_range_tiles_the_queries():
@@ -58,3 +65,60 @@ def test_offsets_allgather_world2(tmp_path):
         assert offset == totals[:r].sum()
         out[offset : offset + len(body)] = body
     assert np.array_equal(out, expected)
+
+
+class _FakeTree:
+    """Stands in for a CellTree2d on a GPU-less host: deterministic fixed-size and variable-length answers per query, so
+    that the sharding / offset / gather logic can be checked against the unsharded call."""
+
+    def locate_points(self, points, tolerance=None):
+        return (np.floor(points[:, 0] * 10) + 100 * np.floor(points[:, 1] * 10)).astype(np.intp)
+
+    def intersect_boxes(self, boxes):
+        counts = (np.floor(boxes[:, 0] * 7) % 4).astype(np.intp)  # 0..3 pairs per box
+        i = np.repeat(np.arange(len(boxes), dtype=np.intp), counts)
+        j = (np.floor(boxes[i, 1] * 1000)).astype(np.intp) + np.concatenate([np.arange(c) for c in counts] or [np.empty(0, int)])
+        return i, j, boxes[i, 2] * 0.5
+
+
+def _sharded_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tree = _FakeTree()
+        rng = np.random.default_rng(11)
+        points = rng.uniform(0, 1, (1003, 2))
+        boxes = rng.uniform(0, 1, (777, 4))
+        lo, hi, found = locate_points_sharded(tree, points)
+        np.save(os.path.join(tmp, f"points{rank}.npy"), np.concatenate([[lo, hi], found]))
+        gi, j, area, offset, total = query_pairs_sharded(tree, "intersect_boxes", boxes)
+        gathered = gather_pairs(gi, j, area, offset, total, dst=0)
+        if rank == 0:
+            np.savez(os.path.join(tmp, "gathered.npz"), i=gathered[0], j=gathered[1], area=gathered[2])
+        else:
+            assert gathered is None
+        with pytest.raises(ValueError):
+            query_pairs_sharded(tree, "locate_faces", boxes)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_queries_reproduce_the_unsharded_order_world2(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    tree = _FakeTree()
+    rng = np.random.default_rng(11)
+    points = rng.uniform(0, 1, (1003, 2))
+    boxes = rng.uniform(0, 1, (777, 4))
+    expected = tree.locate_points(points)
+    out = np.full(len(points), -7, dtype=np.intp)
+    for r in range(world):
+        part = np.load(tmp_path / f"points{r}.npy")
+        lo, hi = int(part[0]), int(part[1])
+        out[lo:hi] = part[2:]
+    assert np.array_equal(out, expected)
+    ei, ej, ea = tree.intersect_boxes(boxes)
+    got = np.load(tmp_path / "gathered.npz")
+    assert np.array_equal(got["i"], ei) and np.array_equal(got["j"], ej) and np.array_equal(got["area"], ea)
