@@ -19,57 +19,49 @@ namespace ct {
 //     second queue, and whenever THAT holds 32 the lanes run the expensive half (Cyrus-Beck against the polygon) on one
 //     survivor each; a hit is appended to the log (hitlog.cuh) with the segment, the candidate's ordinal, the cell and
 //     the clipped points, and counted for its segment.
-// After the scan of the counts, k_place_hits_unordered drops every hit somewhere in its segment's range, and the final
-// per-segment sort orders the range by (t, ordinal): the reference's stable sort by t of the hits in emission order
-// (geometry_utils.py:564-574), since the ordinal grows with the emission order.
-// If the log overflows, the second traversal (one thread per segment, k_locate_edges_fill) writes the pairs in emission order.
+// After the scan of the counts, k_place_sources notes for every hit a slot of its segment's range, and k_rank_and_move
+// gives every hit its rank by (t, ordinal) among its segment's hits and moves it from the log to that place: the
+// reference's stable sort by t of the hits in emission order (geometry_utils.py:564-574), since the ordinal grows with the
+// emission order.  Handing the lanes of a warp further segments as they finish (a share of 64 .. 256 segments per warp)
+// was measured and lost: C4 call 47.5 ms with 32 segments per warp, 49.0 / 49.9 / 52.9 ms with 64 / 128 / 256.
+// If the log overflows, the second traversal (one thread per segment, k_locate_edges_fill) writes the pairs in emission
+// order and k_sort_edge_ranges sorts every range in place.
 constexpr int QUEUE_CAP = 64;  // per warp: a step adds at most 32 candidates, a drain starts at 32
 
-// ROUNDS: every warp owns 32 * ROUNDS consecutive slots of the execution order.  All their segments are brought into
-// shared memory up front; a lane whose walk is over picks up the warp's next unstarted segment, so the walks keep (nearly)
-// all 32 lanes busy until the warp's share runs out, instead of the warp waiting for its longest segment with ever fewer
-// lanes walking.  A candidate's `owner` is the index of its segment within the warp's share.
-template <int MAXV, int ROUNDS>
+template <int MAXV>
 __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const double *__restrict__ edges, int64_t n,
                                                              int32_t *__restrict__ counts, const uint32_t *__restrict__ perm,
                                                              HitLog log) {
     constexpr int WARPS = BLOCK / 32;
-    constexpr int SHARE = 32 * ROUNDS;
-    static_assert(SHARE <= 256, "owner indices are stored in a byte");
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ double2 s_segment[WARPS][SHARE][2];
-    __shared__ int32_t s_hits[WARPS][SHARE];
-    __shared__ int32_t s_query[WARPS][SHARE];
+    __shared__ double2 s_segment[WARPS][32][2];
+    __shared__ int32_t s_hits[WARPS][32];
     __shared__ int32_t s_cell[WARPS][QUEUE_CAP], s_ordinal[WARPS][QUEUE_CAP];    // candidates
     __shared__ uint8_t s_owner[WARPS][QUEUE_CAP];
     __shared__ int32_t s_cell2[WARPS][QUEUE_CAP], s_ordinal2[WARPS][QUEUE_CAP];  // candidates that passed the box clip
     __shared__ uint8_t s_owner2[WARPS][QUEUE_CAP];
     const int warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31u;
-    const int64_t share_base = ((int64_t)blockIdx.x * WARPS + warp) * SHARE;
-    const int share = n - share_base >= SHARE ? SHARE : (n > share_base ? (int)(n - share_base) : 0);
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int k = r * 32 + (int)lane;
-        int32_t q = 0;
-        double2 a2 = make_double2(0.0, 0.0), b2 = a2;
-        if (k < share) {
-            q = perm ? (int32_t)__ldg(perm + share_base + k) : (int32_t)(share_base + k);
-            const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * (int64_t)q;
-            a2 = __ldg(e);
-            b2 = __ldg(e + 1);
-        }
-        s_segment[warp][k][0] = a2;
-        s_segment[warp][k][1] = b2;
-        s_query[warp][k] = q;
-        s_hits[warp][k] = 0;
+    const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = slot < n;
+    const int64_t q = valid ? (perm ? (int64_t)__ldg(perm + slot) : slot) : 0;
+    P2 a{0.0, 0.0}, b{0.0, 0.0};
+    if (valid) {
+        const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
+        const double2 a2 = __ldg(e), b2 = __ldg(e + 1);
+        a = P2{a2.x, a2.y};
+        b = P2{b2.x, b2.y};
     }
-    __syncwarp();
-    const Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
-    int handed = 0;  // warp-uniform: segments of the share handed out so far
-    int mine = 0;  // the segment this lane is walking (index within the share)
-    P2 a{0.0, 0.0}, b{0.0, 0.0}, V{0.0, 0.0};
+    s_segment[warp][lane][0] = make_double2(a.x, a.y);
+    s_segment[warp][lane][1] = make_double2(b.x, b.y);
+    s_hits[warp][lane] = 0;
     bool active = false;
+    if (valid) {
+        P2 c, d;
+        Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
+        active = cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d) != 0;
+    }
+    const P2 V = to_vector(a, b);
     const char *base = reinterpret_cast<const char *>(t.treelets);
     uint32_t stack[STACK_CAP];
     int sp = 0;
@@ -79,31 +71,10 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     int ordinal = 0;   // candidates of this segment pushed so far
     int queued = 0;    // entries in the warp's queues (warp-uniform)
     int queued2 = 0;
+    __syncwarp();
     while (true) {
-        // ---- idle lanes take the next unstarted segments of the share ---------------------------------------------------
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle != 0u && handed < share) {
-            if (!active) {
-                const int k = handed + __popc(idle & ((1u << lane) - 1u));
-                if (k < share) {
-                    mine = k;
-                    const double2 a2 = s_segment[warp][k][0], b2 = s_segment[warp][k][1];
-                    a = P2{a2.x, a2.y};
-                    b = P2{b2.x, b2.y};
-                    V = to_vector(a, b);
-                    P2 c, d;
-                    active = cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d) != 0;  // query.py:369-372
-                    sp = 0;
-                    leaf_k = 0;
-                    ordinal = 0;
-                    cursor_enter(cur, base, ROOT_HANDLE);
-                }
-            }
-            handed += __popc(idle);
-            if (handed > share) handed = share;
-        }
         const bool walking = __any_sync(FULL, active);
-        if (!walking && queued == 0 && queued2 == 0 && handed >= share) break;
+        if (!walking && queued == 0 && queued2 == 0) break;
         // ---- one node per walking lane ------------------------------------------------------------------------------
         bool push = false;
         int cell = 0;
@@ -148,19 +119,20 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
             const int at = queued + __popc(pushing & ((1u << lane) - 1u));
             s_cell[warp][at] = cell;
             s_ordinal[warp][at] = ordinal++;
-            s_owner[warp][at] = (uint8_t)mine;
+            s_owner[warp][at] = (uint8_t)lane;
         }
         queued += __popc(pushing);
         __syncwarp();
         // ---- 32 candidates at a time, one per lane ----------------------------------------------------------------
-        const bool last = !__any_sync(FULL, active) && handed >= share;
+        const bool last = !__any_sync(FULL, active);
         // second stage: the expensive half on (up to) 32 survivors; `flush` also takes a partial batch
         auto clip_survivors = [&](bool flush) {
             while (queued2 >= 32 || (flush && queued2 > 0)) {
                 const int take2 = queued2 < 32 ? queued2 : 32;
                 const int first2 = queued2 - take2;
                 const bool mine2 = (int)lane < take2;
-                const int owner2 = mine2 ? s_owner2[warp][first2 + lane] : 0;
+                const int owner2 = mine2 ? s_owner2[warp][first2 + lane] : (int)lane;
+                const int64_t owner_q = __shfl_sync(FULL, q, owner2);
                 if (mine2) {
                     const int cell2 = s_cell2[warp][first2 + lane];
                     const double2 a2 = s_segment[warp][owner2][0], b2 = s_segment[warp][owner2][1];
@@ -171,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
                     if (hit) {
                         const int64_t at = hitlog_reserve(log);
                         if (at < log.capacity) {
-                            log.q[at] = s_query[warp][owner2];
+                            log.q[at] = (int32_t)owner_q;
                             log.k[at] = s_ordinal2[warp][first2 + lane];
                             log.j[at] = cell2;
                             double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
@@ -188,10 +160,10 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
         while (queued >= 32 || (last && queued > 0)) {
             const int take = queued < 32 ? queued : 32;
             const int first = queued - take;
-            const bool mine1 = (int)lane < take;
+            const bool mine = (int)lane < take;
             bool pass = false;
-            int bbox_index = 0, owner = 0, ordinal_of = 0;
-            if (mine1) {
+            int bbox_index = 0, owner = (int)lane, ordinal_of = 0;
+            if (mine) {
                 owner = s_owner[warp][first + lane];
                 bbox_index = s_cell[warp][first + lane];
                 ordinal_of = s_ordinal[warp][first + lane];
@@ -213,30 +185,7 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
         }
         if (last) clip_survivors(true);  // the walks are over and the first queue is empty: flush
     }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int k = r * 32 + (int)lane;
-        if (k < share) counts[s_query[warp][k]] = s_hits[warp][k];
-    }
-}
-
-// log entry -> some free place of its segment's range (the sort orders the range); `ordinal` keeps what the sort needs
-__global__ void __launch_bounds__(256) k_place_hits_unordered(HitLog log, int64_t entries, const int64_t *__restrict__ offsets,
-                                                              int32_t *__restrict__ filled, int32_t *__restrict__ out_i,
-                                                              int32_t *__restrict__ out_j, double *__restrict__ out_xy,
-                                                              int32_t *__restrict__ ordinal) {
-    int64_t at = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (at >= entries) return;
-    const int32_t q = __ldcs(log.q + at);
-    const int64_t to = offsets[q] + atomicAdd(filled + q, 1);
-    out_i[to] = q;
-    out_j[to] = __ldcs(log.j + at);
-    ordinal[to] = __ldcs(log.k + at);
-    const double2 *in = reinterpret_cast<const double2 *>(log.xy + 4 * at);
-    double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
-    o[0] = __ldcs(in);
-    o[1] = __ldcs(in + 1);
+    if (valid) counts[q] = s_hits[warp][lane];
 }
 
 // log entry -> some free slot of its segment's range, which only records WHERE in the log the hit is (4 bytes) and whose
@@ -368,26 +317,6 @@ int64_t hit_log_per_query() {
     return g_hit_log;
 }
 
-// CELLTREE_EDGE_PLACEMENT=sort: the earlier scheme (hits dropped anywhere in their range, then an insertion sort per range)
-static bool placement_by_rank() {
-    static int by_rank = -1;
-    if (by_rank < 0) {
-        const char *e = getenv("CELLTREE_EDGE_PLACEMENT");
-        by_rank = (e && e[0] == 's') ? 0 : 1;
-    }
-    return by_rank == 1;
-}
-
-static int edge_rounds() {
-    static int rounds = 0;
-    if (rounds == 0) {
-        const char *e = getenv("CELLTREE_EDGE_ROUNDS");
-        const int r = e ? atoi(e) : 4;
-        rounds = r <= 1 ? 1 : (r == 2 ? 2 : (r <= 4 ? 4 : 8));
-    }
-    return rounds;
-}
-
 template <int MAXV>
 static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_result *r, cudaStream_t s) {
     TreeView v = tree->view();
@@ -403,12 +332,7 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     CT_CHECK(buffers.alloc(n, hit_log_per_query(), true, s));
     const HitLog &log = buffers.log;
     if (n > 0) {
-        // segments per warp = 32 x rounds; measured on C4 (10 M segments), ms of this launch: see DESIGN.md 4.4
-        const int rounds = edge_rounds();
-        if (rounds == 1) k_edges_cooperative<MAXV, 1><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
-        else if (rounds == 2) k_edges_cooperative<MAXV, 2><<<grid_for(n, BLOCK * 2), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
-        else if (rounds == 4) k_edges_cooperative<MAXV, 4><<<grid_for(n, BLOCK * 4), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
-        else k_edges_cooperative<MAXV, 8><<<grid_for(n, BLOCK * 8), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
+        k_edges_cooperative<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -418,7 +342,7 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     r->size = total;
     r->width = 4;
     if (n > 0 && total > 0) {
-        if (total <= log.capacity && placement_by_rank()) {
+        if (total <= log.capacity) {
             // every hit is in the log: note where (one slot per hit in its segment's range), then rank and move
             Scratch<uint32_t> source;
             CT_CHECK(source.alloc(total, s));
@@ -428,16 +352,11 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
             k_rank_and_move<<<grid_for(total, 256), 256, 0, s>>>(log, d_edges, total, offsets.p, source.p, r->i, r->j, r->payload);
             CT_LAUNCH_CHECK();
         } else {
+            // the log overflowed: second traversal, pairs in emission order, then the per-segment insertion sort
             Scratch<int32_t> ordinal;
             CT_CHECK(ordinal.alloc(total, s));
-            if (total <= log.capacity) {
-                CT_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)n, s));
-                k_place_hits_unordered<<<grid_for(total, 256), 256, 0, s>>>(log, total, offsets.p, counts.p, r->i, r->j, r->payload,
-                                                                           ordinal.p);
-            } else {  // the log overflowed: second traversal, pairs in emission order
-                k_locate_edges_fill<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
-                                                                              ordinal.p, order.perm);
-            }
+            k_locate_edges_fill<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
+                                                                          ordinal.p, order.perm);
             CT_LAUNCH_CHECK();
             k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload, ordinal.p);
             CT_LAUNCH_CHECK();

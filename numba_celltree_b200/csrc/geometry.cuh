@@ -271,11 +271,14 @@ static __device__ __noinline__ int cohen_sutherland_line_box_clip(P2 a, P2 b, Bo
     while ((k1 | k2) != CS_INSIDE) {
         if ((k1 & k2) != 0) return 0;
         int opt = k1 ? k1 : k2;
-        double x, y;
-        if (opt & CS_UPPER) { x = a.x + dx * (box.ymax - a.y) / dy; y = box.ymax; }
-        else if (opt & CS_LOWER) { x = a.x + dx * (box.ymin - a.y) / dy; y = box.ymin; }
-        else if (opt & CS_RIGHT) { y = a.y + dy * (box.xmax - a.x) / dx; x = box.xmax; }
-        else { y = a.y + dy * (box.xmin - a.x) / dx; x = box.xmin; }
+        // The four cases of cohen_sutherland.py:71-84 (upper, lower, right, left, in that priority) are one expression
+        // with the operands exchanged: moved = along + (slope * (bound - across)) / run.  Selecting the operands and
+        // dividing once keeps the lanes of a warp together (one division sequence instead of four divergent ones); the
+        // operations and their order are the reference's, so the bits are.
+        const bool horizontal = (opt & (CS_UPPER | CS_LOWER)) != 0;  // clip against y = bound, else against x = bound
+        const double bound = (opt & CS_UPPER) ? box.ymax : ((opt & CS_LOWER) ? box.ymin : ((opt & CS_RIGHT) ? box.xmax : box.xmin));
+        const double moved = (horizontal ? a.x : a.y) + ((horizontal ? dx : dy) * (bound - (horizontal ? a.y : a.x))) / (horizontal ? dy : dx);
+        const double x = horizontal ? moved : bound, y = horizontal ? bound : moved;
         if (opt == k1) { a = P2{x, y}; k1 = get_clip(a, box); }
         else if (opt == k2) { b = P2{x, y}; k2 = get_clip(b, box); }
         dx = b.x - a.x;

@@ -3,9 +3,9 @@
 // "Count, then fill" runs the traversal twice.  Where the per-candidate test is expensive (the segment clips of
 // intersect_edges) the first pass instead counts the
 // hits of every query AND appends each hit (query, rank within the query, cell[, payload]) to a log, in whatever order
-// the warps get there; after the scan of the counts a placement kernel moves every entry to offsets[query] + rank, which
-// is the reference's order (query ascending, emission order within a query).  If the log's capacity does not suffice,
-// the caller falls back to the second traversal, which writes the pairs in place.
+// the warps get there; after the scan of the counts the caller moves every entry into its query's range of the result
+// (edges.cu: k_place_sources + k_rank_and_move), which restores the reference's order.  If the log's capacity does not
+// suffice, the caller falls back to the second traversal, which writes the pairs in place.
 #pragma once
 
 #include "common.cuh"
@@ -28,24 +28,6 @@ __device__ __forceinline__ int64_t hitlog_reserve(const HitLog &log) {
     if ((int)lane == leader) first = atomicAdd(log.count, (unsigned long long)__popc(mask));
     first = __shfl_sync(mask, first, leader);
     return (int64_t)first + __popc(mask & ((1u << lane) - 1u));
-}
-
-// log entry -> its place in the result
-static __global__ void __launch_bounds__(256) k_place_hits(HitLog log, int64_t entries, const int64_t *__restrict__ offsets,
-                                                           int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
-                                                           double *__restrict__ out_xy) {
-    int64_t at = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (at >= entries) return;
-    const int32_t q = __ldcs(log.q + at);
-    const int64_t to = offsets[q] + __ldcs(log.k + at);
-    out_i[to] = q;
-    out_j[to] = __ldcs(log.j + at);
-    if (log.xy) {
-        const double2 *in = reinterpret_cast<const double2 *>(log.xy + 4 * at);
-        double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
-        o[0] = __ldcs(in);
-        o[1] = __ldcs(in + 1);
-    }
 }
 
 // Owns the log's device buffers for the duration of a call.

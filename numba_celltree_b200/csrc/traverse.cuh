@@ -258,9 +258,18 @@ CT_DEV bool edge_edge_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
 
 // ---- locate_edge, query.py:357-455 --------------------------------------------------------------------------
 // Which children of the inner node under the cursor the segment a -> b (V = b - a) may reach: the parametric test of
-// the planes Lmax / Rmin along the segment, query.py:407-440.  Written without branches (both quotients are always
-// formed and then selected) so that the lanes of a warp stay together; the values are those of the reference's
-// nested ifs: a quotient is only USED under the conditions under which the reference computes it.
+// the planes Lmax / Rmin along the segment, query.py:407-440.
+//
+// The reference first sets left = (dx_left >= 0), right = (dx_right <= 0) and then, where such a flag is set and dx != 0,
+// replaces it by a test of the parameter t = dx_left / dx (forward, dx > 0: t >= 0; backward, dx < 0: 1 - t >= 0; for the
+// right plane: t <= 1, resp. 1 - t <= 1).  With FINITE operands those second tests cannot fail:
+//   forward:  dx_left >= 0, dx > 0  =>  t is +-0 or positive (or +0 by underflow)     =>  t >= 0;
+//             dx_right <= 0          =>  t is +-0 or negative (-inf by overflow)        =>  t <= 1;
+//   backward: dx_left >= 0, dx < 0  =>  t <= 0 or -0  =>  1 - t >= 1                   =>  1 - t >= 0;
+//             dx_right <= 0          =>  t >= 0 or +0 (+inf by overflow)  =>  1 - t <= 1.
+// (IEEE division gives the quotient the XOR of the signs, and -0.0 >= 0.0 holds.)  Only an infinite operand can change
+// the outcome (inf / inf = NaN fails every comparison), so the two divisions -- 8 % of the instructions of
+// intersect_edges' first pass (profiles/r01_edges_cooperative_ncu.txt) -- are formed on that path alone.
 CT_DEV void edge_plane_test(const Cursor &cur, P2 a, P2 b, P2 V, bool &left, bool &right) {
     const bool dim = cursor_dim(cur);
     const double Lmax = cur.plane.x, Rmin = cur.plane.y;
@@ -270,11 +279,16 @@ CT_DEV void edge_plane_test(const Cursor &cur, P2 a, P2 b, P2 V, bool &left, boo
     const bool forward = dx > 0.0, backward = dx < 0.0;
     const double dx_left = Lmax - (forward ? a_d : b_d);
     const double dx_right = Rmin - (forward ? b_d : a_d);
-    const double t_left = dx_left / dx, t_right = dx_right / dx;
-    const bool left_t = forward ? (t_left >= 0.0) : (backward ? ((1.0 - t_left) >= 0.0) : true);
-    const bool right_t = forward ? (t_right <= 1.0) : (backward ? ((1.0 - t_right) <= 1.0) : true);
-    left = (dx_left >= 0.0) && left_t;
-    right = (dx_right <= 0.0) && right_t;
+    left = dx_left >= 0.0;
+    right = dx_right <= 0.0;
+    const bool finite = fabs(dx) <= FLOAT_MAX && fabs(dx_left) <= FLOAT_MAX && fabs(dx_right) <= FLOAT_MAX;  // false for NaN
+    if (!finite) {
+        const double t_left = dx_left / dx, t_right = dx_right / dx;
+        const bool left_t = forward ? (t_left >= 0.0) : (backward ? ((1.0 - t_left) >= 0.0) : true);
+        const bool right_t = forward ? (t_right <= 1.0) : (backward ? ((1.0 - t_right) <= 1.0) : true);
+        left = left && left_t;
+        right = right && right_t;
+    }
 }
 
 // MAXV == 0 selects the edge-edge test (EdgeCellTree2d), otherwise the edge-face test with that polygon bound.

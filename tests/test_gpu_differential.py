@@ -187,6 +187,54 @@ def test_edges(delaunay_pair):
     assert np.array_equal(xy, rxy, equal_nan=True)
 
 
+def test_edges_with_extreme_coordinates(pkg, delaunay_pair):
+    """Segments whose plane test leaves the finite case (infinite / overflowing / NaN coordinates), axis-parallel and
+    degenerate segments, subnormal offsets: the division-free plane test must decide exactly as query.py:407-440 does.
+    Both code paths of intersect_edges (log, and second traversal) and both tree kinds are covered."""
+    from numba_celltree_b200 import _lib
+    from numba_celltree_b200.synthetic import random_network
+
+    tree, ref, vertices, faces = delaunay_pair
+    rng = np.random.default_rng(17)
+    n = 4000
+    a = rng.uniform(-0.2, 1.2, (n, 2))
+    b = rng.uniform(-0.2, 1.2, (n, 2))
+    special = np.array([np.inf, -np.inf, np.nan, 1e308, -1e308, 1.7e308, 5e-324, -5e-324, 0.0, -0.0, 1e-300, 0.5, 2.0])
+    which = rng.integers(0, 4, n)
+    value = special[rng.integers(0, len(special), n)]
+    a[which == 0, 0] = value[which == 0]
+    a[which == 1, 1] = value[which == 1]
+    b[which == 2, 0] = value[which == 2]
+    b[which == 3, 1] = value[which == 3]
+    both = rng.random(n) < 0.3  # a second special coordinate on the other end point
+    b[both, 0] = special[rng.integers(0, len(special), int(both.sum()))]
+    edges = np.stack((a, b), axis=1)
+    axis = rng.uniform(0, 1, (2000, 2, 2))
+    axis[:1000, 1, 0] = axis[:1000, 0, 0]  # vertical
+    axis[1000:, 1, 1] = axis[1000:, 0, 1]  # horizontal
+    on_vertices = np.stack((vertices[rng.integers(0, len(vertices), 1000)], vertices[rng.integers(0, len(vertices), 1000)]), axis=1)
+    edges = np.concatenate([edges, axis, on_vertices, on_vertices[:, ::-1], np.repeat(on_vertices[:50, :1], 2, axis=1)])
+    ri, rj, rxy = ref.intersect_edges(edges)
+    assert len(ri) > 1000
+    try:
+        for per_query in (16, 0):
+            _lib.check(_lib.load().ct_set_hit_log(per_query))
+            i, j, xy = tree.intersect_edges(edges)
+            assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(xy, rxy, equal_nan=True)
+    finally:
+        _lib.check(_lib.load().ct_set_hit_log(-1))
+    net_vertices, net_edges = random_network(3000, seed=4)
+    net = pkg.EdgeCellTree2d(net_vertices, net_edges)
+    net_ref = oracle.EdgeCellTree2d(net_vertices, net_edges)
+    lo, hi = net_vertices.min(), net_vertices.max()
+    scaled = edges.copy()
+    finite = np.isfinite(scaled) & (np.abs(scaled) < 1e3)
+    scaled[finite] = lo + scaled[finite] * (hi - lo)
+    i, j, xy = net.intersect_edges(scaled)
+    ri, rj, rxy = net_ref.intersect_edges(scaled)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(xy, rxy, equal_nan=True)
+
+
 def test_boxes_and_edges_with_a_short_or_absent_hit_log(pkg, delaunay_pair):
     """The hit log is an execution detail: overflowing it (or having none) falls back to the second traversal."""
     from numba_celltree_b200 import _lib
