@@ -129,3 +129,15 @@ def check_edge_tree(EdgeCellTree2d, name):
     assert np.array_equal(i, g["intersect_edges_i"]), f"{name} intersect_edges i"
     assert np.array_equal(j, g["intersect_edges_j"]), f"{name} intersect_edges j"
     assert_close(xy, g["intersect_edges_xy"], f"{name} intersect_edges xy")
+
+
+def check_extreme_segments(CellTree2d, EdgeCellTree2d):
+    """`extreme_segments.npz` (tests/golden/make_golden_extreme.py): infinite / NaN / overflowing / subnormal / axis-parallel
+    query segments through intersect_edges of both tree kinds, against the reference's own output."""
+    g = load("extreme_segments")
+    i, j, xy = CellTree2d(g["face_vertices"], g["face_faces"], -1).intersect_edges(g["face_segments"])
+    assert np.array_equal(i, g["face_i"]) and np.array_equal(j, g["face_j"]), "extreme segments: face pairs"
+    assert_close(xy, g["face_xy"], "extreme segments: face clip coordinates")
+    i, j, xy = EdgeCellTree2d(g["net_vertices"], g["net_edges"]).intersect_edges(g["net_segments"])
+    assert np.array_equal(i, g["net_i"]) and np.array_equal(j, g["net_j"]), "extreme segments: network pairs"
+    assert_close(xy, g["net_xy"], "extreme segments: network intersection points")

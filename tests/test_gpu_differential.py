@@ -187,6 +187,7 @@ def test_edges(delaunay_pair):
     assert np.array_equal(xy, rxy, equal_nan=True)
 
 
+@pytest.mark.filterwarnings("ignore:overflow encountered", "ignore:invalid value encountered")  # t of a hit on an overflowing segment
 def test_edges_with_extreme_coordinates(pkg, delaunay_pair):
     """Segments whose plane test leaves the finite case (infinite / overflowing / NaN coordinates), axis-parallel and
     degenerate segments, subnormal offsets: the division-free plane test must decide exactly as query.py:407-440 does.

@@ -46,3 +46,8 @@ def test_faces(pkg, name):
 @pytest.mark.parametrize("name", G.EDGE_CASES)
 def test_edge_tree(pkg, name):
     G.check_edge_tree(pkg.EdgeCellTree2d, name)
+
+
+@pytest.mark.filterwarnings("ignore:overflow encountered", "ignore:invalid value encountered")  # t of a hit on an overflowing segment
+def test_extreme_segments(pkg):
+    G.check_extreme_segments(pkg.CellTree2d, pkg.EdgeCellTree2d)

@@ -34,3 +34,8 @@ def test_faces(name):
 @pytest.mark.parametrize("name", G.EDGE_CASES)
 def test_edge_tree(name):
     G.check_edge_tree(oracle.EdgeCellTree2d, name)
+
+
+@pytest.mark.filterwarnings("ignore:overflow encountered", "ignore:invalid value encountered")  # t of a hit on an overflowing segment
+def test_extreme_segments():
+    G.check_extreme_segments(oracle.CellTree2d, oracle.EdgeCellTree2d)
