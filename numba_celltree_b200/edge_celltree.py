@@ -11,7 +11,7 @@ import numpy as np
 
 from numba_celltree_b200 import _lib
 from numba_celltree_b200.cast import cast_edges, cast_vertices
-from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree
+from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _is_cuda_tensor, _ptr
 from numba_celltree_b200.constants import MIN_TOLERANCE, TOLERANCE_FACTOR, FloatArray, IntArray, IntDType
 
 
@@ -63,13 +63,24 @@ class EdgeCellTree2d(CellTree2dBase):
         return self._locate_points(points, tolerance, with_weights=False)
 
     def intersect_edges(self, edge_coords: FloatArray) -> Tuple[IntArray, IntArray, FloatArray]:
-        """Pairs (edge index, tree edge index) and the intersection point, ordered per edge along the edge."""
-        edge_coords = cast_edges(edge_coords)
+        """Pairs (edge index, tree edge index) and the intersection point, ordered per edge along the edge.
+        A float64 CUDA tensor of shape ``(n_edge, 2, 2)`` is read in place and the results are CUDA tensors."""
+        device = None
+        if _is_cuda_tensor(edge_coords):
+            if edge_coords.dim() != 3 or tuple(edge_coords.shape[1:]) != (2, 2) or str(edge_coords.dtype) != "torch.float64":
+                raise ValueError("edges must have shape (n_edge, 2, 2)")
+            edge_coords = edge_coords.contiguous()
+            device = edge_coords.device
+        else:
+            edge_coords = cast_edges(edge_coords)
         handle = ctypes.c_void_p()
         _lib.check(
             _lib.load().ct_intersect_edges(
-                self._tree.handle, edge_coords.ctypes.data, edge_coords.shape[0], _lib.CT_MEM_HOST, ctypes.byref(handle)
+                self._tree.handle, _ptr(edge_coords), edge_coords.shape[0],
+                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
             )
-        )
-        i, j, xy = self._fetch(handle, payload_shape=(2, 2))
+        )  # fmt: skip
+        i, j, xy = self._fetch(handle, payload_shape=(2, 2), device=device)
+        if device is not None:
+            return i, j, xy[:, 0].contiguous()
         return i, j, np.ascontiguousarray(xy[:, 0])

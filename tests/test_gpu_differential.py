@@ -164,6 +164,31 @@ def test_device_resident_query_mesh_matches_host(delaunay_pair):
         tree.intersect_faces(dqv, dqf.to(torch.int32), -1)
 
 
+def test_device_resident_network_queries_match_host(pkg):
+    """EdgeCellTree2d with CUDA tensors: locate_points and intersect_edges give the host path's results, on the device."""
+    torch = pytest.importorskip("torch")
+    from numba_celltree_b200.synthetic import random_network
+
+    vertices, edges = random_network(4000, seed=12)
+    net = pkg.EdgeCellTree2d(vertices, edges)
+    rng = np.random.default_rng(6)
+    lo, hi = vertices.min(axis=0), vertices.max(axis=0)
+    a = rng.uniform(lo, hi, (30_000, 2))
+    segments = np.stack((a, a + rng.normal(0, 3.0, a.shape)), axis=1)
+    i, j, xy = net.intersect_edges(segments)
+    di, dj, dxy = net.intersect_edges(torch.from_numpy(segments).cuda())
+    assert len(i) > 1000 and di.is_cuda and dxy.is_cuda and dxy.shape == (len(i), 2)
+    assert np.array_equal(di.cpu().numpy(), i) and np.array_equal(dj.cpu().numpy(), j)
+    assert np.array_equal(dxy.cpu().numpy(), xy, equal_nan=True)
+    on_network = 0.5 * (vertices[edges[:, 0]] + vertices[edges[:, 1]])
+    points = np.concatenate([on_network, rng.uniform(lo, hi, (20_000, 2))])
+    found = net.locate_points(points)
+    d_found = net.locate_points(torch.from_numpy(points).cuda())
+    assert (found >= 0).sum() >= len(on_network) and np.array_equal(d_found.cpu().numpy(), found)
+    with pytest.raises(ValueError):
+        net.intersect_edges(torch.zeros((5, 4), dtype=torch.float64, device="cuda"))
+
+
 def test_boxes(delaunay_pair):
     tree, ref, _, faces = delaunay_pair
     boxes = c3_boxes(len(faces), 300_000)
