@@ -16,7 +16,7 @@ import numpy as np
 from numba_celltree_b200 import _lib
 from numba_celltree_b200.cast import cast_bboxes, cast_edges, cast_faces, cast_vertices, check_faces_shape
 from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _is_cuda_tensor, _ptr
-from numba_celltree_b200.constants import FloatArray, IntArray, IntDType, NodeDType
+from numba_celltree_b200.constants import FloatArray, IntArray, IntDType
 
 
 class CellTree2d(CellTree2dBase):

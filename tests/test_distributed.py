@@ -1,11 +1,9 @@
 """Host-side sharding logic of the multi-GPU path, world_size 2 over gloo on CPU."""
 
 import os
-import sys
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 

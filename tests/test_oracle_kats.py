@@ -3,7 +3,7 @@
 import numpy as np
 
 import oracle
-from tests import _golden, _reference_kats as K
+from tests import _reference_kats as K
 
 
 def test_init_and_casting():
