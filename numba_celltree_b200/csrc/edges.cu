@@ -1,6 +1,6 @@
 // edges.cu -- ct_intersect_edges: warp-cooperative traversal of the query segments that counts and logs the hits
-// (Cohen-Sutherland + Cyrus-Beck against faces, segment/segment against a network), scan, placement, and the
-// per-segment sort by (t, emission ordinal).
+// (Cohen-Sutherland + Cyrus-Beck against faces, segment/segment against a network), scan, and the placement of
+// every hit at its rank by (t, emission ordinal) within its segment's range.
 #include "hitlog.cuh"
 #include "morton.cuh"
 #include "traverse.cuh"
