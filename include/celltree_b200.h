@@ -182,6 +182,30 @@ int32_t ct_result_payload_width(const ct_result *result); /* doubles per pair: 0
 int ct_result_fetch(const ct_result *result, int64_t *i, int64_t *j, double *payload, int32_t mem);
 void ct_result_free(ct_result *result);
 
+/* ---- geometry helpers the reference exports beside the query API ----------------------
+ * The reference's versions are scalar @njit functions on Point / Box tuples; these take n inputs per call.
+ * a, b, c, d: (n, 2) doubles; intersects / inside: n bytes (0 / 1); c, d are NaN where intersects is 0.
+ * boxes: (n_boxes, 4) rows (xmin, xmax, ymin, ymax) with n_boxes == n (one box per segment) or 1 (one box for all).
+ *   ct_liang_barsky_line_box_clip      algorithms/liang_barsky.py:10-64
+ *   ct_cohen_sutherland_line_box_clip  algorithms/cohen_sutherland.py:36-101
+ *   ct_cyrus_beck_line_polygon_clip    algorithms/cyrus_beck.py:143-241 (polygon: (n_polygon, 2), counter-clockwise, convex,
+ *                                      3..32 vertices; all segments against the one polygon)
+ *   ct_points_in_polygon               geometry_utils.py:98-147 point_in_polygon (no tolerance), all points against one polygon
+ *   ct_points_in_triangles             geometry_utils.py:273-289 (faces: (n_face, n_max_vert) int64, the first three columns
+ *                                      are the triangle; face_indices: n int64; an index out of range is CT_ERR_VALUE)
+ * ct_profile_binning: diagnostics, device milliseconds of the spatial binning of ct_locate_points alone (points on the device). */
+int ct_liang_barsky_line_box_clip(const double *a, const double *b, const double *boxes, int64_t n_boxes, int64_t n,
+                                  uint8_t *intersects, double *c, double *d, int32_t mem);
+int ct_cohen_sutherland_line_box_clip(const double *a, const double *b, const double *boxes, int64_t n_boxes, int64_t n,
+                                      uint8_t *intersects, double *c, double *d, int32_t mem);
+int ct_cyrus_beck_line_polygon_clip(const double *a, const double *b, int64_t n, const double *polygon, int32_t n_polygon,
+                                    double tolerance, uint8_t *intersects, double *c, double *d, int32_t mem);
+int ct_points_in_polygon(const double *points, int64_t n, const double *polygon, int32_t n_polygon, uint8_t *inside, int32_t mem);
+int ct_points_in_triangles(const double *points, const int64_t *face_indices, int64_t n, const int64_t *faces, int64_t n_face,
+                           int32_t n_max_vert, const double *vertices, int64_t n_vertex, double tolerance, uint8_t *inside,
+                           int32_t mem);
+int ct_profile_binning(const ct_tree *tree, const double *points, int64_t n, int32_t repeats, double *ms_per_run);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,12 @@ _SIGNATURES = {
     "ct_result_payload_width": (c_i32, [c_void_p]),
     "ct_result_fetch": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32]),
     "ct_result_free": (None, [c_void_p]),
+    "ct_liang_barsky_line_box_clip": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_cohen_sutherland_line_box_clip": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_cyrus_beck_line_polygon_clip": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i32, c_f64, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_points_in_polygon": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_i32, c_void_p, c_i32]),
+    "ct_points_in_triangles": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_void_p, c_i64, c_f64, c_void_p, c_i32]),
+    "ct_profile_binning": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, ctypes.POINTER(c_f64)]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

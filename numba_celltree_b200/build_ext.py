@@ -17,8 +17,8 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libcelltree_b200.so"
-SOURCES = [CSRC / name for name in ("lib.cu", "points.cu", "boxes.cu", "edges.cu", "build.cu")]
-HEADERS = [CSRC / "common.cuh", CSRC / "geometry.cuh", CSRC / "traverse.cuh", CSRC / "morton.cuh", HERE.parent / "include" / "celltree_b200.h"]
+SOURCES = [CSRC / name for name in ("lib.cu", "points.cu", "boxes.cu", "edges.cu", "build.cu", "algorithms.cu")]
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted((HERE.parent / "include").glob("*.h"))  # every header: a stale .so must never be used
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

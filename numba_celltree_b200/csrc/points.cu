@@ -1,7 +1,11 @@
-// points.cu -- ct_locate_points: Morton ordering of the queries, the traversal kernel (entry grid, treelet descent,
-// point-in-polygon test, fused barycentric weights at the hit; four points per thread), results written in execution
-// order and un-permuted through one radix pass; for host buffers a chunked three-stream pipeline around it.
-#include "morton.cuh"
+// points.cu -- ct_locate_points.  Large batches: the points are binned by a 16-bit Z-order key (binning.cuh), the
+// traversal kernel takes tiles of 2048 binned records, orders each tile in shared memory and walks the tree (entry
+// grid, treelet descent, point-in-polygon test, fused barycentric weights at the hit); results return through
+// per-window queues.  Small batches: one kernel in the caller's order.  For host buffers a chunked three-stream
+// pipeline around either.
+#include <cub/block/block_radix_sort.cuh>
+
+#include "binning.cuh"
 #include "traverse.cuh"
 
 namespace ct {
@@ -100,6 +104,128 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
     else __stcs(out + i, (int64_t)found);
 }
 
+// ---- the traversal over binned records -----------------------------------------------------------------------------
+// One block = one tile of TILE consecutive records (binning.cuh).  The tile is sorted by the key bits below the bin
+// (as many as the tile spans: 8 + log2(bins in the tile)), then thread t walks the tree for the sorted positions
+// t, t + 256, ...: a warp's 32 points are neighbours along the Z-order curve.  MAXV == 0: EdgeCellTree2d.
+#ifndef CT_EXP2
+#define CT_EXP2 0
+#endif
+#ifndef CT_TILE_MINB
+#define CT_TILE_MINB 4  // blocks per SM of the 3- and 4-vertex kernels (64 registers)
+#endif
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_ITEMS = 8;
+constexpr int TILE = TILE_THREADS * TILE_ITEMS;
+
+using TileSort = cub::BlockRadixSort<uint16_t, TILE_THREADS, TILE_ITEMS, uint16_t>;
+struct TileShared {
+    typename TileSort::TempStorage sort;
+    uint32_t span, key0;
+};
+
+template <int MAXV, bool WEIGHTS, int MINB>
+__global__ void __launch_bounds__(TILE_THREADS, MINB)
+    k_locate_points_binned(TreeView t, const PointRecord *__restrict__ records, int64_t n, double tolerance,
+                           uint2 *__restrict__ pairs, uint32_t *__restrict__ window_cursor, int64_t *__restrict__ out,
+                           double *__restrict__ weights) {
+    __shared__ TileShared sh;
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    const int m = (int)((n - base) < TILE ? (n - base) : TILE);
+    const PointRecord *tile = records + base;
+    if (threadIdx.x == 0) {
+        sh.span = 0;
+        // the records are in bin order, so no key of the tile is below its first record's bin
+        sh.key0 = (__ldg(&tile[0].key) >> FINE_BITS) << FINE_BITS;
+    }
+    __syncthreads();
+    // Only the keys are read for the sort (the records stay in L2 for the second read below): key relative to the
+    // tile's first bin, saturating.  Which thread holds which item does not matter to a sort; `source` says where
+    // the item sits in the tile.
+    const uint32_t key0 = sh.key0;
+    uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
+    uint32_t span = 0;
+#pragma unroll
+    for (int k = 0; k < TILE_ITEMS; k++) {
+        const int j = k * TILE_THREADS + threadIdx.x;
+        uint32_t rel = 0xffffu;
+        if (j < m) {
+            rel = __ldg(&tile[j].key) - key0;
+            rel = rel < 0xffffu ? rel : 0xffffu;
+            span = rel > span ? rel : span;
+        }
+        keys[k] = (uint16_t)rel;
+        source[k] = (uint16_t)j;
+    }
+    span = __reduce_max_sync(0xffffffffu, span);
+    if ((threadIdx.x & 31) == 0) atomicMax(&sh.span, span);
+    __syncthreads();
+#if CT_EXP2 == 2
+    const int bits = 0;
+#else
+    const int bits = 32 - __clz(sh.span | 1u);
+#endif
+    TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, bits);
+    // thread t now holds the sorted positions t, t + 256, ...: a warp's 32 points are neighbours on the Z-order curve.
+    // The record of the next position is requested while the tree is walked for the current one, and so is the
+    // slot in the result queue of the query's window (an atomic whose answer is only needed after the walk).
+    uint64_t order_lo = 0, order_hi = 0;  // source[] packed, so that the loop below can stay rolled without a local array
+#pragma unroll
+    for (int k = 0; k < TILE_ITEMS; k++) {
+        if (k < 4) order_lo |= (uint64_t)source[k] << (16 * k);
+        else order_hi |= (uint64_t)source[k] << (16 * (k - 4));
+    }
+    static_assert(TILE_ITEMS == 8, "source[] is packed into two 64-bit words");
+    double x, y;
+    uint32_t index, key;
+    int j = (int)(order_lo & 0xffffu);
+    if (j < m) load_record(tile + j, x, y, index, key);
+#pragma unroll 1
+    for (int k = 0; k < TILE_ITEMS; k++) {
+        const bool valid = j < m;
+        const P2 p{x, y};
+        const uint32_t my_index = index;
+        if (k + 1 < TILE_ITEMS) {
+            j = (int)(((k + 1 < 4 ? order_lo : order_hi) >> (16 * ((k + 1) & 3))) & 0xffffu);
+            if (j < m) load_record(tile + j, x, y, index, key);
+        }
+        if (!valid) continue;
+        uint32_t slot = 0;
+#if CT_EXP2 != 1
+        if (pairs) slot = atomicAdd(window_cursor + (my_index >> WINDOW_BITS), 1u);
+#endif
+        int found;
+        if constexpr (MAXV == 0) found = locate_point_on_edge(t, p, tolerance);
+        else found = locate_point<MAXV>(t, p, tolerance);
+        // (index, result) -> the queue of the index's window; small batches: straight to out (L2 merges the stores)
+#if CT_EXP2 == 1
+        if (pairs) pairs[base + k * TILE_THREADS + threadIdx.x] = make_uint2(my_index, (uint32_t)found);
+#else
+        if (pairs) pairs[((int64_t)(my_index >> WINDOW_BITS) << WINDOW_BITS) + slot] = make_uint2(my_index, (uint32_t)found);
+#endif
+        else out[my_index] = (int64_t)found;
+        if constexpr (WEIGHTS) write_weights<MAXV, WEIGHTS>(t, found, p, tolerance, weights + (int64_t)my_index * t.M);
+    }
+}
+
+template <int MAXV>
+static int launch_locate_points_binned(const TreeView &v, const PointRecord *records, int64_t n, double tol, uint2 *pairs,
+                                       uint32_t *window_cursor, int64_t *out, double *weights, cudaStream_t s) {
+    const int grid = grid_for(n, TILE);
+    auto launch = [&](auto kernel) -> int {
+        kernel<<<grid, TILE_THREADS, 0, s>>>(v, records, n, tol, pairs, window_cursor, out, weights);
+        return CT_OK;
+    };
+    if (weights) {
+        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, 2>));
+    } else if (MAXV <= 4)
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB>));
+    else
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, 2>));
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
 template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
                                 const uint32_t *perm, int32_t *in_order, cudaStream_t s) {
@@ -116,33 +242,57 @@ static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n
     return CT_OK;
 }
 
+// batches up to this many queries write their results straight to out[index]: the 8-byte stores of a batch whose
+// result array (8 n bytes) stays in L2 merge there; larger batches go through the window queues
+static int64_t direct_out_limit() {
+    static int64_t limit = -1;
+    if (limit < 0) {
+        const char *e = getenv("CELLTREE_DIRECT_OUT");
+        limit = e ? atoll(e) : ((int64_t)1 << 22);
+    }
+    return limit;
+}
+
 static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
                                 cudaStream_t s, bool profile = false) {
     if (n == 0) return CT_OK;
     TreeView v = tree->view();
     PhaseEvents *ev = profile ? phase_events() : nullptr;
     if (ev) CT_CUDA(cudaEventRecord(ev->start, s));
-    MortonOrder order;
-    CT_CHECK(order.build<KEY_POINT>(tree, reinterpret_cast<const double *>(pts), n, s));
-    const uint32_t *perm = order.perm;
-    static int two_phase = -1;
-    if (two_phase < 0) {
-        const char *e = getenv("CELLTREE_SCATTER");
-        two_phase = (e && e[0] == 'd') ? 0 : 1;  // "direct": results are stored straight to out[perm[t]]
+    const bool binned = sort_bits_for(tree, n) > 0;
+    if (!binned) {
+        // the caller's order: small batches, small trees
+        if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
+        int status = CT_OK;
+        if (tree->kind == CT_KIND_EDGES) {
+            k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, nullptr, nullptr);
+            CT_LAUNCH_CHECK();
+        } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
+        else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
+        else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
+        else status = launch_locate_points<32>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
+        if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
+        return status;
     }
-    int32_t *in_order = (perm && two_phase) ? reinterpret_cast<int32_t *>(order.spare[0]) : nullptr;
+    PointBins bins;
+    CT_CHECK(bins.build(tree, pts, n, s));
+    Scratch<uint2> pairs;
+    const bool queued = n > direct_out_limit();
+    if (queued) CT_CHECK(pairs.alloc(n, s));
     if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
     int status;
-    if (tree->kind == CT_KIND_EDGES) {
-        k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, perm, in_order);
-        CT_LAUNCH_CHECK();
-        status = CT_OK;
-    } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, perm, in_order, s);
-    else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, perm, in_order, s);
-    else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, perm, in_order, s);
-    else status = launch_locate_points<32>(v, pts, n, tol, out, weights, perm, in_order, s);
+    uint32_t *wc = bins.window_cursor();
+    if (tree->kind == CT_KIND_EDGES) status = launch_locate_points_binned<0>(v, bins.records.p, n, tol, pairs.p, wc, out, nullptr, s);
+    else if (tree->M == 3) status = launch_locate_points_binned<3>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
+    else if (tree->M == 4) status = launch_locate_points_binned<4>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
+    else if (tree->M <= 8) status = launch_locate_points_binned<8>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
+    else status = launch_locate_points_binned<32>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
     if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
-    if (status == CT_OK && in_order) status = order.scatter_results(n, out, s);
+    if (status == CT_OK && queued) {
+        CT_CUDA(cudaFuncSetAttribute(k_windows_to_out, cudaFuncAttributeMaxDynamicSharedMemorySize, WINDOW * (int)sizeof(int32_t)));
+        k_windows_to_out<<<(unsigned)bins.n_windows, WINDOW_THREADS, WINDOW * sizeof(int32_t), s>>>(pairs.p, n, out);
+        CT_LAUNCH_CHECK();
+    }
     return status;
 }
 
@@ -230,3 +380,33 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
     return status;
 }
 
+
+// Diagnostics: device time of the binning alone (count + offsets + scatter) over `repeats` runs, points on the device.
+extern "C" int ct_profile_binning(const ct_tree *tree, const double *points, int64_t n, int32_t repeats, double *ms_per_run) {
+    if (!tree || !points || n <= 0 || repeats <= 0 || !ms_per_run) {
+        set_error("ct_profile_binning: bad argument");
+        return CT_ERR_VALUE;
+    }
+    CT_CUDA(cudaSetDevice(tree->device));
+    cudaStream_t s = current_stream();
+    cudaEvent_t e0, e1;
+    CT_CUDA(cudaEventCreate(&e0));
+    CT_CUDA(cudaEventCreate(&e1));
+    {
+        PointBins warm;
+        CT_CHECK(warm.build(tree, reinterpret_cast<const double2 *>(points), n, s));
+    }
+    CT_CUDA(cudaEventRecord(e0, s));
+    for (int r = 0; r < repeats; r++) {
+        PointBins bins;
+        CT_CHECK(bins.build(tree, reinterpret_cast<const double2 *>(points), n, s));
+    }
+    CT_CUDA(cudaEventRecord(e1, s));
+    CT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_run = ms / repeats;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return CT_OK;
+}

@@ -610,6 +610,123 @@ void orc_wachspress(const double *polygon, int n, double px, double py, double *
     wachspress_compute_weights((const pt *)polygon, n, p, weights, n_w, tol);
 }
 
+/* ------------------------------------------------------------------ */
+/* Exported helpers off the API path, batched        */
+/* ------------------------------------------------------------------ */
+static inline int point_inside_box(pt a, box_t box)                                      /* geometry_utils.py:527-529 */
+{
+    return box.xmin < a.x && a.x < box.xmax && box.ymin < a.y && a.y < box.ymax;
+}
+
+/* algorithms/liang_barsky.py:10-64: parametric clip of a -> b against the four box sides, taken in the order
+ * left, right, lower, upper; a segment of zero length, or one that only touches (t0 == t1), is a miss. */
+static int liang_barsky_line_box_clip(pt a, pt b, box_t box, pt *c, pt *d)
+{
+    const double nan_ = NAN;
+    c->x = c->y = d->x = d->y = nan_;
+    double dx = b.x - a.x, dy = b.y - a.y;
+    if (dx == 0.0 && dy == 0.0) return 0;
+    if (point_inside_box(a, box) && point_inside_box(b, box)) { *c = a; *d = b; return 1; }
+    double t0 = 0.0, t1 = 1.0;
+    const double P[4] = { -dx, dx, -dy, dy };
+    const double Q[4] = { a.x - box.xmin, box.xmax - a.x, a.y - box.ymin, box.ymax - a.y };
+    for (int i = 0; i < 4; i++) {
+        double p_i = P[i], q_i = Q[i];
+        if (p_i == 0) {
+            if (q_i < 0) return 0;              /* parallel to this side and outside of it */
+        } else {
+            double t = q_i / p_i;
+            if (p_i < 0) {
+                if (t > t1) return 0;
+                else if (t > t0) t0 = t;
+            } else if (p_i > 0) {
+                if (t < t0) return 0;
+                else if (t < t1) t1 = t;
+            }
+        }
+    }
+    if (t0 == t1) return 0;
+    c->x = a.x + t0 * dx; c->y = a.y + t0 * dy;
+    d->x = a.x + t1 * dx; d->y = a.y + t1 * dy;
+    return 1;
+}
+
+void orc_liang_barsky(const double *a, const double *b, const double *boxes, int64_t n, uint8_t *hit, double *c, double *d)
+{
+    for (int64_t i = 0; i < n; i++) {
+        pt pa = { a[2 * i], a[2 * i + 1] }, pb = { b[2 * i], b[2 * i + 1] }, pc, pd;
+        hit[i] = (uint8_t)liang_barsky_line_box_clip(pa, pb, as_box(boxes + 4 * i), &pc, &pd);
+        c[2 * i] = pc.x; c[2 * i + 1] = pc.y; d[2 * i] = pd.x; d[2 * i + 1] = pd.y;
+    }
+}
+
+void orc_cohen_sutherland_batch(const double *a, const double *b, const double *boxes, int64_t n, uint8_t *hit, double *c, double *d)
+{
+    for (int64_t i = 0; i < n; i++) {
+        pt pa = { a[2 * i], a[2 * i + 1] }, pb = { b[2 * i], b[2 * i + 1] }, pc, pd;
+        hit[i] = (uint8_t)cohen_sutherland_line_box_clip(pa, pb, as_box(boxes + 4 * i), &pc, &pd);
+        c[2 * i] = pc.x; c[2 * i + 1] = pc.y; d[2 * i] = pd.x; d[2 * i + 1] = pd.y;
+    }
+}
+
+void orc_cyrus_beck_batch(const double *a, const double *b, int64_t n, const double *poly, int length, double tol,
+                          uint8_t *hit, double *c, double *d)
+{
+    for (int64_t i = 0; i < n; i++) {
+        pt pa = { a[2 * i], a[2 * i + 1] }, pb = { b[2 * i], b[2 * i + 1] }, pc, pd;
+        hit[i] = (uint8_t)cyrus_beck_line_polygon_clip(pa, pb, (const pt *)poly, length, tol, &pc, &pd);
+        c[2 * i] = pc.x; c[2 * i + 1] = pc.y; d[2 * i] = pd.x; d[2 * i + 1] = pd.y;
+    }
+}
+
+/* geometry_utils.py:98-147: the plain crossing-number test (no tolerance, no on-edge acceptance) */
+static int point_in_polygon(pt p, const pt *poly, int length)
+{
+    pt v0 = poly[length - 1];
+    int inside = 0;
+    for (int i = 0; i < length; i++) {
+        pt v1 = poly[i];
+        if (((v0.y > p.y) != (v1.y > p.y)) && (p.x < ((v1.x - v0.x) * (p.y - v0.y) / (v1.y - v0.y) + v0.x))) inside = !inside;
+        v0 = v1;
+    }
+    return inside;
+}
+
+void orc_points_in_polygon(const double *points, int64_t n, const double *poly, int length, uint8_t *inside)
+{
+    for (int64_t i = 0; i < n; i++) {
+        pt p = { points[2 * i], points[2 * i + 1] };
+        inside[i] = (uint8_t)point_in_polygon(p, (const pt *)poly, length);
+    }
+}
+
+/* geometry_utils.py:241-270: half-plane signs first, then the three on-edge tests */
+static int point_in_triangle(pt p, pt ta, pt tb, pt tc, double tolerance)
+{
+    pt ap = to_vector(ta, p), bp = to_vector(tb, p), cp = to_vector(tc, p);
+    pt ab = to_vector(ta, tb), bc = to_vector(tb, tc), ca = to_vector(tc, ta);
+    double A = cross_product(ab, ap), B = cross_product(bc, bp), C = cross_product(ca, cp);
+    int sA = A > 0, sB = B > 0, sC = C > 0;
+    if (sA == sB && sB == sC) return 1;
+    if ((within_perpendicular_distance(A, ab, tolerance) && in_bounds(p, ta, tb))
+        || (within_perpendicular_distance(B, bc, tolerance) && in_bounds(p, tb, tc))
+        || (within_perpendicular_distance(C, ca, tolerance) && in_bounds(p, tc, ta)))
+        return 1;
+    return 0;
+}
+
+/* geometry_utils.py:273-289 */
+void orc_points_in_triangles(const double *points, const int64_t *face_indices, int64_t n, const int64_t *faces,
+                             int64_t n_max_vert, const double *vertices, double tolerance, uint8_t *inside)
+{
+    const pt *v = (const pt *)vertices;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t *face = faces + face_indices[i] * n_max_vert;
+        pt p = { points[2 * i], points[2 * i + 1] };
+        inside[i] = (uint8_t)point_in_triangle(p, v[face[0]], v[face[1]], v[face[2]], tolerance);
+    }
+}
+
 /* ================================================================== */
 /* Mesh preparation: geometry_utils.py                                 */
 /* ================================================================== */
