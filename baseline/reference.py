@@ -15,7 +15,7 @@ import sys
 import time
 
 HERE = pathlib.Path(__file__).resolve().parent
-REF_ROOT = HERE / "_ref"
+REF_ROOT = pathlib.Path(os.environ.get("CELLTREE_REFERENCE_ROOT") or HERE / "_ref")  # the override is for the fallback test
 
 
 def host_threads() -> int:

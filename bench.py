@@ -229,7 +229,7 @@ def run_reference(args):
     import reference as ref_arm
 
     nx, n_points, name = workload()
-    budget_s = float(os.environ.get("CELLTREE_BENCH_REFERENCE_BUDGET_S", 150))
+    budget_s = float(os.environ.get("CELLTREE_BENCH_REFERENCE_BUDGET_S", 240))
     vertices, faces = quad_mesh(nx, nx)
     info = {}
     fallback = None
@@ -277,8 +277,7 @@ def run_reference(args):
     rate = len(probe) / max(time.perf_counter() - t0, 1e-9)
     calls = args.steps + args.warmup + 2  # + the API calls below
     forced = os.environ.get("CELLTREE_BENCH_REFERENCE_SAMPLE")
-    sample = int(forced) if forced else int(rate * budget_s / calls)
-    sample = max(min(n_points, sample), min(n_points, 1_000_000))
+    sample = min(n_points, int(forced)) if forced else max(min(n_points, int(rate * budget_s / calls)), min(n_points, 1_000_000))
     points = c2_points(sample)  # a prefix of the seed-42 stream == the first `sample` points the GPU arm steps over
     for _ in range(args.warmup):
         kernel_call(points)

@@ -1,6 +1,6 @@
 """
-The driver-facing contract of bench.py that can be checked without a GPU: the reference arm (the CPU restatement of the
-reference's algorithm on the host cores) prints exactly one JSON line on stdout with the agreed keys, on rank 0 only.
+The driver-facing contract of bench.py that can be checked without a GPU: the reference arm (the unmodified reference under Numba on the host
+cores; the C port only as a declared fallback) prints exactly one JSON line on stdout with the agreed keys, on rank 0 only.
 Sizes are cut down through the environment so the test takes seconds.
 """
 
@@ -29,9 +29,22 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["vs_baseline"] is None and line["dtype"] == "f64"
     assert "workload" in line["config"] and "64x64" in line["config"]["workload"]
     cpu = line["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "50000" in cpu["sample"]
+    assert cpu["cores"] >= 1 and cpu["value"] == line["value"] and "50000" in cpu["sample"]
+    if (ROOT / "baseline" / "_ref" / "numba_celltree").is_dir():
+        # the unmodified reference, vendored by baseline/vendor_ref.py, under Numba
+        assert cpu["kind"] == "reference" and "fallback" not in line and cpu["numba_threads"] >= 1 and cpu["threading_layer"]
+        assert "query.locate_points" in line["config"]["timed_call"] and line["config"]["api_equals_kernel_result"] is True
+    else:
+        assert cpu["kind"] == "port" and "fallback" in line
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_falls_back_to_the_port_and_says_so():
+    done = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", CELLTREE_REFERENCE_ROOT="/nonexistent")
+    assert done.returncode == 0, done.stderr[-2000:]
+    line = json.loads(done.stdout.strip())
+    assert line["cpu_baseline"]["kind"] == "port" and "reference unavailable" in line["fallback"]
 
 
 def test_reference_arm_is_silent_on_other_ranks():
