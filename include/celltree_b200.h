@@ -68,7 +68,7 @@ typedef struct ct_tree_info {
     int32_t n_buckets;
     int32_t cells_per_leaf;
     int32_t depth;            /* number of node levels (root alone = 1) */
-    int32_t reserved;
+    int32_t device;           /* CUDA device the tree lives on */
     double bbox[4];           /* bbox_tree(), celltree_base.py:20-25 */
     double default_tolerance; /* default_tolerance(bb_distances[:, 2]), celltree_base.py:51-52 */
     double build_ms;          /* device time of the build (CUDA events) */
@@ -131,6 +131,12 @@ int ct_tree_get_info(const ct_tree *tree, ct_tree_info *info);
  * (after counter_clockwise); bb_distances: n_elem x 3 (dx, dy, diagonal). */
 int ct_tree_download(const ct_tree *tree, ct_node41 *nodes, int64_t *bb_indices, double *bb_coords,
                      int64_t *elements, double *bb_distances, int32_t mem);
+
+/* Replace the tree's node array by an edited copy (n_nodes must be the tree's own) and derive the traversal structures
+ * again.  The reference's queries read tree.nodes on every call (query.py:73), so editing that array changes the answers
+ * (tests/test_celltree.py:606-618); the Python classes call this entry when the caller has modified the `nodes` mirror.
+ * Links that are out of range or do not follow their parent are refused (CT_ERR_VALUE) and the tree is left unchanged. */
+int ct_tree_update_nodes(ct_tree *tree, const ct_node41 *nodes, int64_t n_nodes, int32_t mem);
 
 void ct_tree_destroy(ct_tree *tree);
 

@@ -42,7 +42,7 @@ class TreeInfo(ctypes.Structure):
         ("n_buckets", c_i32),
         ("cells_per_leaf", c_i32),
         ("depth", c_i32),
-        ("reserved", c_i32),
+        ("device", c_i32),
         ("bbox", c_f64 * 4),
         ("default_tolerance", c_f64),
         ("build_ms", c_f64),
@@ -72,6 +72,7 @@ _SIGNATURES = {
     ),
     "ct_tree_get_info": (ctypes.c_int, [c_void_p, ctypes.POINTER(TreeInfo)]),
     "ct_tree_download": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32]),
+    "ct_tree_update_nodes": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32]),
     "ct_tree_destroy": (None, [c_void_p]),
     "ct_locate_points": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_f64, c_void_p, c_void_p, c_i32]),
     "ct_locate_boxes": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, ctypes.POINTER(c_void_p)]),

@@ -15,7 +15,7 @@ import numpy as np
 
 from numba_celltree_b200 import _lib
 from numba_celltree_b200.cast import cast_bboxes, cast_edges, cast_faces, cast_vertices, check_faces_shape
-from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _is_cuda_tensor, _ptr
+from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _aligned, _is_cuda_tensor, _ptr
 from numba_celltree_b200.constants import FloatArray, IntArray, IntDType
 
 
@@ -91,23 +91,17 @@ class CellTree2d(CellTree2dBase):
         return self._locate_points(points, tolerance, with_weights=True)
 
     def _boxes(self, bbox_coords, with_area: bool):
-        lib = _lib.load()
         device = None
         if _is_cuda_tensor(bbox_coords):
             if bbox_coords.dim() != 2 or bbox_coords.shape[1] != 4 or str(bbox_coords.dtype) != "torch.float64":
                 raise ValueError("bbox_coords must have shape (n_box, 4)")
-            bbox_coords = bbox_coords.contiguous()
+            bbox_coords = _aligned(bbox_coords)
             device = bbox_coords.device
         else:
             bbox_coords = cast_bboxes(bbox_coords)
-        handle = ctypes.c_void_p()
-        _lib.check(
-            lib.ct_locate_boxes(
-                self._tree.handle, _ptr(bbox_coords), bbox_coords.shape[0], int(with_area),
-                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
-            )
-        )  # fmt: skip
-        return self._fetch(handle, payload_shape=(), device=device)
+        return self._variable(
+            "ct_locate_boxes", _ptr(bbox_coords), bbox_coords.shape[0], int(with_area), tensors=(bbox_coords,), device=device
+        )
 
     def locate_boxes(self, bbox_coords: FloatArray) -> Tuple[IntArray, IntArray]:
         """Pairs (box index, face index) whose bounding boxes overlap; rows are ``(xmin, xmax, ymin, ymax)``."""
@@ -119,15 +113,10 @@ class CellTree2d(CellTree2dBase):
         return self._boxes(bbox_coords, with_area=True)
 
     def _faces(self, vertices, faces, fill_value: int, write_back: bool, with_area: bool, device=None):
-        handle = ctypes.c_void_p()
-        _lib.check(
-            _lib.load().ct_locate_faces(
-                self._tree.handle, _ptr(vertices), vertices.shape[0], _ptr(faces), faces.shape[0],
-                faces.shape[1], int(fill_value), int(write_back), int(with_area),
-                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
-            )
+        return self._variable(
+            "ct_locate_faces", _ptr(vertices), vertices.shape[0], _ptr(faces), faces.shape[0], faces.shape[1], int(fill_value),
+            int(write_back), int(with_area), tensors=(vertices, faces), device=device,
         )  # fmt: skip
-        return self._fetch(handle, payload_shape=(), device=device)
 
     @staticmethod
     def _device_mesh(vertices, faces):
@@ -141,7 +130,7 @@ class CellTree2d(CellTree2dBase):
         check_faces_shape(faces)
         if vertices.device != faces.device:
             raise ValueError("vertices and faces must be on the same device")
-        return vertices.contiguous(), faces.contiguous()
+        return _aligned(vertices), _aligned(faces)
 
     def locate_faces(self, vertices: FloatArray, faces: IntArray) -> Tuple[IntArray, IntArray]:
         """
@@ -194,15 +183,10 @@ class CellTree2d(CellTree2dBase):
         if _is_cuda_tensor(edge_coords):
             if edge_coords.dim() != 3 or tuple(edge_coords.shape[1:]) != (2, 2) or str(edge_coords.dtype) != "torch.float64":
                 raise ValueError("edges must have shape (n_edge, 2, 2)")
-            edge_coords = edge_coords.contiguous()
+            edge_coords = _aligned(edge_coords)
             device = edge_coords.device
         else:
             edge_coords = cast_edges(edge_coords)
-        handle = ctypes.c_void_p()
-        _lib.check(
-            _lib.load().ct_intersect_edges(
-                self._tree.handle, _ptr(edge_coords), edge_coords.shape[0],
-                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
-            )
-        )  # fmt: skip
-        return self._fetch(handle, payload_shape=(2, 2), device=device)
+        return self._variable(
+            "ct_intersect_edges", _ptr(edge_coords), edge_coords.shape[0], tensors=(edge_coords,), payload_shape=(2, 2), device=device
+        )

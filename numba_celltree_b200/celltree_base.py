@@ -22,6 +22,38 @@ def _is_cuda_tensor(x) -> bool:
     return bool(getattr(x, "is_cuda", False)) and hasattr(x, "data_ptr")
 
 
+class _OnTensorStream:
+    """
+    Binds a device-resident call to the caller's tensors: they must live on the tree's device (a pointer from another GPU
+    would fault inside the kernels), and the library's work is enqueued on torch's CURRENT stream of that device, so that
+    it is ordered after the kernels that produced the inputs and before whatever consumes the results -- also under
+    ``torch.cuda.stream(side)`` -- and a temporary made by ``.contiguous()`` is not reused while a kernel still reads it.
+    """
+
+    def __init__(self, tree: "DeviceTree", *tensors):
+        import torch
+
+        device = int(tree.info.device)
+        for t in tensors:
+            if t is not None and t.device.index != device:
+                raise ValueError(f"the tensor lives on {t.device}, the tree on cuda:{device}")
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+
+    def __enter__(self):
+        _lib.check(_lib.load().ct_set_stream(self.stream))
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _aligned(tensor):
+    """A contiguous tensor whose first byte is 16-byte aligned (the kernels read points and boxes as 16-byte words; a
+    view into the middle of a buffer may start on an odd 8-byte boundary)."""
+    tensor = tensor.contiguous()
+    return tensor if tensor.data_ptr() % 16 == 0 else tensor.clone()
+
+
 def _ptr(a) -> Optional[int]:
     if a is None:
         return None
@@ -30,11 +62,22 @@ def _ptr(a) -> Optional[int]:
     return a.data_ptr()
 
 
+def _checksum(array: np.ndarray):
+    """Wrapping sum and xor over the bytes of a contiguous array taken as 64-bit words (any edit of a field changes them,
+    short of a deliberate collision)."""
+    raw = array.reshape(-1).view(np.uint8)
+    whole = raw[: raw.size // 8 * 8].view(np.uint64)
+    return (int(np.add.reduce(whole, dtype=np.uint64)), int(np.bitwise_xor.reduce(whole)) if whole.size else 0, raw[whole.size * 8 :].tobytes())
+
+
 class DeviceTree:
     """Owner of one ``ct_tree*``."""
 
     def __init__(self, handle: int):
         self.handle = ctypes.c_void_p(handle)
+        self.refresh_info()
+
+    def refresh_info(self):
         info = _lib.TreeInfo()
         _lib.check(_lib.load().ct_tree_get_info(self.handle, ctypes.byref(info)))
         self.info = info
@@ -73,7 +116,25 @@ class CellTree2dBase(abc.ABC):
             args = [out.ctypes.data if key == name else None for key in order]
             _lib.check(_lib.load().ct_tree_download(self._tree.handle, *args, _lib.CT_MEM_HOST))
             cache[name] = out
+            if name == "nodes":
+                self._nodes_checksum = _checksum(out)
         return cache[name]
+
+    def _sync_nodes(self) -> None:
+        """
+        The reference's queries read ``tree.nodes`` on every call (query.py:73), so a caller who edits that array changes
+        the answers (tests/test_celltree.py:606-618).  Here the array is a host mirror of the device tree: once it has
+        been handed out, every query first compares a checksum of it (one pass over the array, about 0.1 ms per MB)
+        and, if it was edited, sends it to the device, which derives its traversal structures again.
+        """
+        nodes = self.__dict__.get("_mirrors", {}).get("nodes")
+        if nodes is None:
+            return
+        now = _checksum(nodes)
+        if now != self._nodes_checksum:
+            _lib.check(_lib.load().ct_tree_update_nodes(self._tree.handle, nodes.ctypes.data, len(nodes), _lib.CT_MEM_HOST))
+            self._nodes_checksum = now
+            self._tree.refresh_info()
 
     @property
     def nodes(self):
@@ -127,6 +188,7 @@ class CellTree2dBase(abc.ABC):
 
         if tolerance is None:
             tolerance = self._default_tolerance()
+        self._sync_nodes()
         lib = _lib.load()
         m = int(self._tree.info.n_max_vert)
         if _is_cuda_tensor(points):
@@ -134,11 +196,13 @@ class CellTree2dBase(abc.ABC):
 
             if points.dtype != torch.float64 or points.dim() != 2 or points.shape[1] != 2:
                 raise ValueError("points must be a float64 CUDA tensor of shape (n_points, 2)")
-            points = points.contiguous()
+            points = _aligned(points)
             n = points.shape[0]
-            out = torch.empty(n, dtype=torch.int64, device=points.device)
-            weights = torch.empty((n, m), dtype=torch.float64, device=points.device) if with_weights else None
-            mem = _lib.CT_MEM_DEVICE
+            with _OnTensorStream(self._tree, points):
+                out = torch.empty(n, dtype=torch.int64, device=points.device)
+                weights = torch.empty((n, m), dtype=torch.float64, device=points.device) if with_weights else None
+                _lib.check(lib.ct_locate_points(self._tree.handle, _ptr(points), n, float(tolerance), _ptr(out), _ptr(weights), _lib.CT_MEM_DEVICE))
+            return (out, weights) if with_weights else out
         else:
             points = cast_vertices(points)
             n = points.shape[0]
@@ -152,6 +216,19 @@ class CellTree2dBase(abc.ABC):
         return (out, weights) if with_weights else out
 
     # ---- variable-length results --------------------------------------------------------------------------------
+    def _variable(self, entry: str, *args, tensors=(), payload_shape=(), device=None):
+        """One variable-length query: `entry(tree, *args, mem, &result)` followed by the fetch of the pairs, on the
+        caller's stream when the inputs are CUDA tensors."""
+        self._sync_nodes()
+        lib = _lib.load()
+        handle = ctypes.c_void_p()
+        if device is None:
+            _lib.check(getattr(lib, entry)(self._tree.handle, *args, _lib.CT_MEM_HOST, ctypes.byref(handle)))
+            return self._fetch(handle, payload_shape=payload_shape)
+        with _OnTensorStream(self._tree, *tensors):
+            _lib.check(getattr(lib, entry)(self._tree.handle, *args, _lib.CT_MEM_DEVICE, ctypes.byref(handle)))
+            return self._fetch(handle, payload_shape=payload_shape, device=device)
+
     @staticmethod
     def _fetch(handle: ctypes.c_void_p, payload_shape=None, device=None):
         lib = _lib.load()

@@ -165,7 +165,7 @@ extern "C" int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t
         return CT_ERR_VALUE;
     }
     CT_CHECK(check_depth(tree));
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     DevIn<double> d_boxes;
     CT_CHECK(d_boxes.init(boxes, (size_t)n * 4, mem, s));
@@ -223,7 +223,7 @@ extern "C" int ct_locate_faces(const ct_tree *tree, const double *vertices, int6
         return CT_ERR_VALUE;
     }
     CT_CHECK(check_depth(tree));
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     const int qM = n_max_vert;
     DevIn<double> d_qv;

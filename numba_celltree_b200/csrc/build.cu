@@ -290,7 +290,7 @@ struct BuildState {
     // elements
     const double *bb;
     int32_t *seg;  // slot of the active node that owns this position, -1 when the position is final
-    uint8_t *bkt;  // bucket of the element at this position (valid where seg >= 0)
+    uint16_t *bkt;  // bucket of the element at this position (valid where seg >= 0); n_buckets <= 65535
     // nodes in creation order
     int32_t *n_ptr, *n_size, *n_child;
     uint8_t *n_dim, *n_tried;
@@ -305,17 +305,37 @@ struct BuildState {
     int32_t *next_active;
     int32_t *counters;  // [0] node count, [1] next active count, [2] error flag
     int nb, cpl;
+    // Signed-zero mode (only when a bounding box holds -0.0, see k_zero_first): position of the first element whose
+    // value equals a zero extreme, per active slot (range) and per (slot, bucket); nullptr otherwise
+    int32_t *a_minpos, *a_maxpos, *b_minpos, *b_maxpos;
 };
+
+// The reference takes extremes with strict comparisons in slice order (get_bounds, creation.py:153-171: `value < Rmin`,
+// `value > Lmax`), so among -0.0 and +0.0 -- equal as numbers, different as bits -- the one met FIRST is kept, and that
+// is what ends up in nodes["Lmax"] / nodes["Rmin"].  The ordered integer image separates the two zeros (-0.0 below
+// +0.0), so atomic min / max would always keep -0.0 / +0.0.  When the boxes hold a -0.0 (a flag computed once per
+// build; otherwise none of this runs), zeros enter the atomics as +0.0, and wherever an extreme comes out as zero the
+// element that supplies it is found by position: k_zero_first takes the minimum position among the elements whose
+// value is a zero, k_zero_apply reads that element's own zero back.
+CT_DEV double unsigned_zero(double v) { return v == 0.0 ? 0.0 : v; }
 
 __global__ void __launch_bounds__(BB) k_init_slots(BuildState st, int n_active) {
     int s = blockIdx.x * BB + threadIdx.x;
     if (s >= n_active) return;
     st.a_min[s] = enc(FLOAT_MAX);   // get_bounds starts from FLOAT_MAX / FLOAT_MIN, creation.py:161-162
     st.a_max[s] = enc(FLOAT_MIN);
+    if (st.a_minpos) {
+        st.a_minpos[s] = INT32_MAX;
+        st.a_maxpos[s] = INT32_MAX;
+    }
     for (int k = 0; k < st.nb; k++) {
         st.b_cnt[(int64_t)s * st.nb + k] = 0;
         st.b_min[(int64_t)s * st.nb + k] = enc(FLOAT_MAX);
         st.b_max[(int64_t)s * st.nb + k] = enc(FLOAT_MIN);
+        if (st.a_minpos) {
+            st.b_minpos[(int64_t)s * st.nb + k] = INT32_MAX;
+            st.b_maxpos[(int64_t)s * st.nb + k] = INT32_MAX;
+        }
     }
 }
 
@@ -336,6 +356,7 @@ __global__ void __launch_bounds__(BB) k_range(BuildState st, const int32_t *__re
         int e = idx[pos];
         double vmin = st.bb[4 * (int64_t)e + 2 * dim];
         double vmax = st.bb[4 * (int64_t)e + 2 * dim + 1];
+        if (st.a_minpos) vmin = unsigned_zero(vmin), vmax = unsigned_zero(vmax);
         if (vmin == vmin) emin = enc(vmin);
         if (vmax == vmax) emax = enc(vmax);
     }
@@ -400,19 +421,36 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
         double bucket_length = (range_Lmax - range_Rmin) / (double)nb;  // creation.py:278
         double centroid = vmin + 0.5 * (vmax - vmin);                    // creation.py:50
         int k = -1;
-        for (int b = 0; b < nb; b++) {
-            double bmax = (double)(b + 1) * bucket_length + range_Rmin;  // creation.py:286
-            double bmin = (double)b * bucket_length + range_Rmin;        // creation.py:287
-            if ((centroid >= bmin) && (centroid < bmax)) {
-                k = b;
-                break;
+        if (nb > 32 && bucket_length > 0.0 && bucket_length <= FLOAT_MAX) {
+            // Many buckets: b -> (double)b * bucket_length + range_Rmin is non-decreasing for a finite positive length
+            // (rounding is monotone), and bmax of bucket b is computed exactly like bmin of bucket b + 1.  So
+            // "centroid < bmax(b)" holds from some first bucket on, "centroid >= bmin(b)" up to some last one, and the
+            // FIRST bucket satisfying both -- what the loop below finds -- is the first one with centroid < bmax(b),
+            // if its bmin test holds too.  A NaN centroid fails every test in both forms.
+            int lo = 0, hi = nb;  // first b in [0, nb) with centroid < bmax(b); nb if none
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double bmax = (double)(mid + 1) * bucket_length + range_Rmin;
+                if (centroid < bmax) hi = mid;
+                else lo = mid + 1;
+            }
+            if (lo < nb && centroid >= (double)lo * bucket_length + range_Rmin) k = lo;
+        } else {
+            for (int b = 0; b < nb; b++) {
+                double bmax = (double)(b + 1) * bucket_length + range_Rmin;  // creation.py:286
+                double bmin = (double)b * bucket_length + range_Rmin;        // creation.py:287
+                if ((centroid >= bmin) && (centroid < bmax)) {
+                    k = b;
+                    break;
+                }
             }
         }
         if (k < 0) {
             atomicExch(st.counters + 2, CT_ERR_UNBUCKETABLE);
             k = nb - 1;
         }
-        st.bkt[pos] = (uint8_t)k;
+        st.bkt[pos] = (uint16_t)k;
+        if (st.a_minpos) vmin = unsigned_zero(vmin), vmax = unsigned_zero(vmax);
         unsigned long long emin = (vmin == vmin) ? enc(vmin) : enc(FLOAT_MAX);
         unsigned long long emax = (vmax == vmax) ? enc(vmax) : enc(FLOAT_MIN);
         if (uniform) {
@@ -437,6 +475,44 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
             }
         }
     }
+}
+
+// Signed-zero mode, after k_bucket: first position per slot / bucket whose value is a zero, where the extreme is zero.
+__global__ void __launch_bounds__(BB) k_zero_first(BuildState st, const int32_t *__restrict__ idx, int64_t n) {
+    const int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (pos >= n) return;
+    const int slot = st.seg[pos];
+    if (slot < 0) return;
+    const int dim = st.n_dim[st.active[slot]];
+    const int e = idx[pos];
+    const double vmin = st.bb[4 * (int64_t)e + 2 * dim], vmax = st.bb[4 * (int64_t)e + 2 * dim + 1];
+    const int64_t o = (int64_t)slot * st.nb + st.bkt[pos];
+    if (vmin == 0.0) {
+        if (dec(st.a_min[slot]) == 0.0) atomicMin(st.a_minpos + slot, (int32_t)pos);
+        if (dec(st.b_min[o]) == 0.0) atomicMin(st.b_minpos + o, (int32_t)pos);
+    }
+    if (vmax == 0.0) {
+        if (dec(st.a_max[slot]) == 0.0) atomicMin(st.a_maxpos + slot, (int32_t)pos);
+        if (dec(st.b_max[o]) == 0.0) atomicMin(st.b_maxpos + o, (int32_t)pos);
+    }
+}
+// ... and the zero of that element, sign included, becomes the extreme
+__global__ void __launch_bounds__(BB) k_zero_apply(BuildState st, const int32_t *__restrict__ idx, int64_t n_entries) {
+    const int64_t q = (int64_t)blockIdx.x * BB + threadIdx.x;  // entry q < n_active: a slot; then (slot, bucket) pairs
+    if (q >= n_entries) return;
+    const int64_t n_slots = n_entries / (st.nb + 1);
+    const bool is_slot = q < n_slots;
+    const int64_t o = is_slot ? q : q - n_slots;
+    const int slot = (int)(is_slot ? q : o / st.nb);
+    const int dim = st.n_dim[st.active[slot]];
+    const int32_t pmin = is_slot ? st.a_minpos[o] : st.b_minpos[o];
+    const int32_t pmax = is_slot ? st.a_maxpos[o] : st.b_maxpos[o];
+    if (pmin != INT32_MAX) (is_slot ? st.a_min : st.b_min)[o] = enc(st.bb[4 * (int64_t)idx[pmin] + 2 * dim]);
+    if (pmax != INT32_MAX) (is_slot ? st.a_max : st.b_max)[o] = enc(st.bb[4 * (int64_t)idx[pmax] + 2 * dim + 1]);
+}
+__global__ void __launch_bounds__(BB) k_any_negative_zero(const double *__restrict__ v, int64_t n, int32_t *__restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * BB + threadIdx.x;
+    if (i < n && __double_as_longlong(v[i]) == (long long)0x8000000000000000ULL) *flag = 1;
 }
 
 CT_DEV void make_node(const BuildState &st, int id, int ptr, int size, int dim) {  // create_node, creation.py:27-29
@@ -559,7 +635,7 @@ __global__ void __launch_bounds__(128) k_decide(BuildState st, int n_active) {
 // one-hot counters of 4 consecutive buckets, scanned over all positions
 struct OneHot4 {
     const int32_t *seg;
-    const uint8_t *bkt;
+    const uint16_t *bkt;
     int group;
     __device__ uint4 operator()(int64_t pos) const {
         uint4 r = make_uint4(0, 0, 0, 0);
@@ -928,7 +1004,8 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
 
     Scratch<int32_t> idx_a, idx_b, seg_a, seg_b, rank, n_ptr, n_size, n_child, act_a, act_b, b_cnt, b_start, next_left, next_right,
         split_pos, counters, splits, pre_rank, final_index, level;
-    Scratch<uint8_t> bkt, n_dim, n_tried;
+    Scratch<uint16_t> bkt;
+    Scratch<uint8_t> n_dim, n_tried;
     Scratch<double> n_Lmax, n_Rmin;
     Scratch<unsigned long long> a_min, a_max, b_min, b_max;
     Scratch<uint4> scan;
@@ -952,10 +1029,15 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     CT_CHECK(act_b.alloc(cap_active, s));
     CT_CHECK(a_min.alloc(cap_active, s));
     CT_CHECK(a_max.alloc(cap_active, s));
-    CT_CHECK(b_cnt.alloc(cap_active * nb, s));
-    CT_CHECK(b_min.alloc(cap_active * nb, s));
-    CT_CHECK(b_max.alloc(cap_active * nb, s));
-    CT_CHECK(b_start.alloc(cap_active * nb, s));
+    // per (active node, bucket) arrays: sized for the waves of a tree with few buckets, grown by a wave that needs more
+    // (n_active * n_buckets entries; with thousands of buckets cap_active * n_buckets would not fit any memory)
+    int64_t cap_buckets = cap_active * nb < 4 * n + 1024 ? cap_active * nb : 4 * n + 1024;
+    CT_CHECK(b_cnt.alloc(cap_buckets, s));
+    CT_CHECK(b_min.alloc(cap_buckets, s));
+    CT_CHECK(b_max.alloc(cap_buckets, s));
+    CT_CHECK(b_start.alloc(cap_buckets, s));
+    Scratch<int32_t> a_minpos, a_maxpos, b_minpos, b_maxpos;  // signed-zero mode only
+    bool signed_zero = false;
     CT_CHECK(next_left.alloc(cap_active, s));
     CT_CHECK(next_right.alloc(cap_active, s));
     CT_CHECK(split_pos.alloc(cap_active, s));
@@ -988,7 +1070,19 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         CT_CUDA(cudaMemcpyAsync(n_Rmin.p, &h_m1, 8, cudaMemcpyHostToDevice, s));
         CT_CUDA(cudaMemcpyAsync(act_a.p, &h_act, 4, cudaMemcpyHostToDevice, s));
         CT_CUDA(cudaMemcpyAsync(counters.p, h_counters, 16, cudaMemcpyHostToDevice, s));
+        // signed-zero mode (k_zero_first) only when some bounding box holds a -0.0
+        k_any_negative_zero<<<grid_for(4 * n, BB), BB, 0, s>>>(tree->bb_coords, 4 * n, counters.p + 3);
+        CT_LAUNCH_CHECK();
+        int32_t h_flag = 0;
+        CT_CUDA(cudaMemcpyAsync(&h_flag, counters.p + 3, 4, cudaMemcpyDeviceToHost, s));
         CT_CUDA(cudaStreamSynchronize(s));  // the host temporaries above go out of scope
+        signed_zero = h_flag != 0;
+    }
+    if (signed_zero) {
+        CT_CHECK(a_minpos.alloc(cap_active, s));
+        CT_CHECK(a_maxpos.alloc(cap_active, s));
+        CT_CHECK(b_minpos.alloc(cap_buckets, s));
+        CT_CHECK(b_maxpos.alloc(cap_buckets, s));
     }
 
     double t_alloc = now_ms();
@@ -1001,6 +1095,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     st.b_cnt = b_cnt.p; st.b_min = b_min.p; st.b_max = b_max.p; st.b_start = b_start.p;
     st.next_left = next_left.p; st.next_right = next_right.p; st.split_pos = split_pos.p;
     st.counters = counters.p;
+    st.a_minpos = a_minpos.p; st.a_maxpos = a_maxpos.p; st.b_minpos = b_minpos.p; st.b_maxpos = b_maxpos.p;
     st.nb = nb; st.cpl = cpl;
 
     int32_t *idx_cur = idx_a.p, *idx_nxt = idx_b.p, *seg_cur = seg_a.p, *seg_nxt = seg_b.p, *act_cur = act_a.p, *act_nxt = act_b.p;
@@ -1011,6 +1106,19 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     const int n_groups = (nb + 3) / 4;
     while (n_active > 0) {
         wave_start.push_back(node_count);
+        if ((int64_t)n_active * nb > cap_buckets) {
+            cap_buckets = (int64_t)n_active * nb;
+            CT_CHECK(b_cnt.alloc(cap_buckets, s));
+            CT_CHECK(b_min.alloc(cap_buckets, s));
+            CT_CHECK(b_max.alloc(cap_buckets, s));
+            CT_CHECK(b_start.alloc(cap_buckets, s));
+            st.b_cnt = b_cnt.p; st.b_min = b_min.p; st.b_max = b_max.p; st.b_start = b_start.p;
+            if (signed_zero) {
+                CT_CHECK(b_minpos.alloc(cap_buckets, s));
+                CT_CHECK(b_maxpos.alloc(cap_buckets, s));
+                st.b_minpos = b_minpos.p; st.b_maxpos = b_maxpos.p;
+            }
+        }
         st.seg = seg_cur;
         st.active = act_cur;
         st.next_active = act_nxt;
@@ -1020,6 +1128,13 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         CT_LAUNCH_CHECK();
         k_bucket<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, n);
         CT_LAUNCH_CHECK();
+        if (signed_zero) {
+            k_zero_first<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, n);
+            CT_LAUNCH_CHECK();
+            const int64_t entries = (int64_t)n_active * (nb + 1);
+            k_zero_apply<<<grid_for(entries, BB), BB, 0, s>>>(st, idx_cur, entries);
+            CT_LAUNCH_CHECK();
+        }
         k_decide<<<grid_for(n_active, 128), 128, 0, s>>>(st, n_active);
         CT_LAUNCH_CHECK();
         for (int g = 0; g < n_groups; g++) {
@@ -1184,8 +1299,8 @@ extern "C" int ct_tree_create(const double *vertices, int64_t n_vertex, const in
         set_error("n_buckets must be >= 2");
         return CT_ERR_VALUE;
     }
-    if (n_buckets > 255) {
-        set_error("n_buckets must be <= 255 in the B200 build");
+    if (n_buckets > 65535) {  // the bucket of an element is kept in 16 bits; the reference has no upper bound (celltree.py:69-72)
+        set_error("n_buckets must be <= 65535");
         return CT_ERR_VALUE;
     }
     if (cells_per_leaf < 1) {
@@ -1238,6 +1353,70 @@ extern "C" int ct_tree_create(const double *vertices, int64_t n_vertex, const in
     return CT_OK;
 }
 
+// nodes (41-byte rows, host or device) -> tree->nodes (already allocated, tree->n_nodes rows) and tree->depth
+static int unpack_nodes(ct_tree *tree, const ct_node41 *nodes, int32_t mem, cudaStream_t s) {
+    const int64_t n_nodes = tree->n_nodes;
+    Scratch<unsigned char> packed;
+    const size_t bytes = (size_t)n_nodes * NODE41;
+    CT_CHECK(packed.alloc(bytes + 4, s));
+    if (mem != CT_MEM_DEVICE) CT_CHECK(upload_from_host(packed.p, nodes, bytes, s));
+    else CT_CUDA(cudaMemcpyAsync(packed.p, nodes, bytes, cudaMemcpyDeviceToDevice, s));
+    k_unpack_nodes<<<grid_for(n_nodes, BB), BB, 0, s>>>(packed.p, n_nodes, tree->nodes);
+    CT_LAUNCH_CHECK();
+    Scratch<int32_t> parent, max_depth;
+    CT_CHECK(parent.alloc(n_nodes, s));
+    CT_CHECK(max_depth.alloc(1, s));
+    k_fill_i32<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, -1);
+    CT_LAUNCH_CHECK();
+    CT_CUDA(cudaMemsetAsync(max_depth.p, 0, 4, s));
+    k_parents<<<grid_for(n_nodes, BB), BB, 0, s>>>(tree->nodes, n_nodes, parent.p);
+    CT_LAUNCH_CHECK();
+    k_depth<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, max_depth.p);
+    CT_LAUNCH_CHECK();
+    int32_t d = 0;
+    CT_CUDA(cudaMemcpyAsync(&d, max_depth.p, 4, cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    tree->depth = d;
+    return CT_OK;
+}
+
+// The reference's queries read tree.nodes on every call (query.py:73), so a caller who edits that array changes the
+// answers (tests/test_celltree.py:606-618 does).  Here the queries read treelets derived from the nodes: this entry
+// replaces the node array by the caller's edited copy and derives the treelets and the entry grid again.  If the new
+// links are refused (a child out of range or not following its parent) the tree keeps its previous state.
+extern "C" int ct_tree_update_nodes(ct_tree *tree, const ct_node41 *nodes, int64_t n_nodes, int32_t mem) {
+    if (!tree || !nodes || n_nodes != tree->n_nodes) {
+        set_error("ct_tree_update_nodes: null argument, or a node count other than the tree's");
+        return CT_ERR_VALUE;
+    }
+    CT_ON_DEVICE(tree->device);
+    cudaStream_t s = current_stream();
+    Node32 *old_nodes = tree->nodes;
+    Treelet *old_treelets = tree->treelets;
+    uint32_t *old_handle = tree->entry_handle;
+    double *old_lo = tree->entry_lo;
+    const int64_t old_n_treelets = tree->n_treelets;
+    const int32_t old_depth = tree->depth, old_bits = tree->entry_bits;
+    tree->nodes = nullptr, tree->treelets = nullptr, tree->entry_handle = nullptr, tree->entry_lo = nullptr;
+    auto body = [&]() -> int {
+        CT_CHECK(dalloc(&tree->nodes, (size_t)n_nodes, s));
+        CT_CHECK(unpack_nodes(tree, nodes, mem, s));
+        CT_CHECK(build_treelets(tree, s));
+        CT_CHECK(build_entry_grid(tree, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+        return CT_OK;
+    };
+    const int status = body();
+    if (status != CT_OK) {
+        dfree(tree->nodes, s), dfree(tree->treelets, s), dfree(tree->entry_handle, s), dfree(tree->entry_lo, s);
+        tree->nodes = old_nodes, tree->treelets = old_treelets, tree->entry_handle = old_handle, tree->entry_lo = old_lo;
+        tree->n_treelets = old_n_treelets, tree->depth = old_depth, tree->entry_bits = old_bits;
+        return status;
+    }
+    dfree(old_nodes, s), dfree(old_treelets, s), dfree(old_handle, s), dfree(old_lo, s);
+    return CT_OK;
+}
+
 extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, const int64_t *elements, int64_t n_elem,
                                    int32_t n_max_vert, int32_t kind, const ct_node41 *nodes, int64_t n_nodes,
                                    const int64_t *bb_indices, const double *bb_coords, int32_t cells_per_leaf, int32_t mem,
@@ -1278,26 +1457,7 @@ extern "C" int ct_tree_from_arrays(const double *vertices, int64_t n_vertex, con
                 src = tmp.p;
             }
             CT_CHECK(launch_narrow(src, n_elem, tree->bb_indices, s));
-            Scratch<unsigned char> packed;
-            size_t bytes = (size_t)n_nodes * NODE41;
-            CT_CHECK(packed.alloc(bytes + 4, s));
-            CT_CHECK(copy_in(packed.p, nodes, bytes));
-            k_unpack_nodes<<<grid_for(n_nodes, BB), BB, 0, s>>>(packed.p, n_nodes, tree->nodes);
-            CT_LAUNCH_CHECK();
-            Scratch<int32_t> parent, max_depth;
-            CT_CHECK(parent.alloc(n_nodes, s));
-            CT_CHECK(max_depth.alloc(1, s));
-            k_fill_i32<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, -1);
-            CT_LAUNCH_CHECK();
-            CT_CUDA(cudaMemsetAsync(max_depth.p, 0, 4, s));
-            k_parents<<<grid_for(n_nodes, BB), BB, 0, s>>>(tree->nodes, n_nodes, parent.p);
-            CT_LAUNCH_CHECK();
-            k_depth<<<grid_for(n_nodes, BB), BB, 0, s>>>(parent.p, n_nodes, max_depth.p);
-            CT_LAUNCH_CHECK();
-            int32_t d = 0;
-            CT_CUDA(cudaMemcpyAsync(&d, max_depth.p, 4, cudaMemcpyDeviceToHost, s));
-            CT_CUDA(cudaStreamSynchronize(s));
-            tree->depth = d;
+            CT_CHECK(unpack_nodes(tree, nodes, mem, s));
         }
         CT_CHECK(finish_bounds(tree, s));
         CT_CHECK(finish_query_data(tree, s));
@@ -1326,7 +1486,7 @@ extern "C" int ct_tree_get_info(const ct_tree *tree, ct_tree_info *info) {
     info->n_buckets = tree->n_buckets;
     info->cells_per_leaf = tree->cells_per_leaf;
     info->depth = tree->depth;
-    info->reserved = 0;
+    info->device = tree->device;
     for (int k = 0; k < 4; k++) info->bbox[k] = tree->bbox[k];
     info->default_tolerance = tree->default_tolerance;
     info->build_ms = tree->build_ms;
@@ -1339,7 +1499,7 @@ extern "C" int ct_tree_download(const ct_tree *tree, ct_node41 *nodes, int64_t *
         set_error("ct_tree_download: null tree");
         return CT_ERR_VALUE;
     }
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     cudaMemcpyKind kind = mem == CT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const int64_t n = tree->n_elem;

@@ -122,6 +122,25 @@ void count_launch(int n = 1);
         CT_CUDA(cudaGetLastError());      \
     } while (0)
 
+// Entry points work on the tree's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int previous = -1;
+    cudaError_t error = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        error = cudaGetDevice(&previous);
+        if (error == cudaSuccess && previous != device) error = cudaSetDevice(device);
+        else previous = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (previous >= 0) cudaSetDevice(previous);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define CT_ON_DEVICE(device)          \
+    ct::DeviceGuard _device_guard(device); \
+    CT_CUDA(_device_guard.error)
+
 // Device memory comes from a caching pool inside the library (lib.cu): blocks are rounded to a few size classes per
 // octave, freed blocks are kept and handed out again in stream order, so a query call does no cudaMalloc / cudaFree
 // (and none of the driver pool's remapping, which cost 20 ms per call for 2 GB of results) once the sizes have been seen.

@@ -382,7 +382,7 @@ extern "C" int ct_intersect_edges(const ct_tree *tree, const double *edges, int6
         return CT_ERR_VALUE;
     }
     CT_CHECK(check_depth(tree));
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     DevIn<double> d_edges;
     CT_CHECK(d_edges.init(edges, (size_t)n * 4, mem, s));

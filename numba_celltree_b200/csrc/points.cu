@@ -311,7 +311,7 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         return CT_ERR_VALUE;
     }
     CT_CHECK(check_depth(tree));
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     if (mem == CT_MEM_DEVICE)
         return locate_points_device(tree, reinterpret_cast<const double2 *>(points), n, tolerance, out_index, weights, s, true);
@@ -387,7 +387,7 @@ extern "C" int ct_profile_binning(const ct_tree *tree, const double *points, int
         set_error("ct_profile_binning: bad argument");
         return CT_ERR_VALUE;
     }
-    CT_CUDA(cudaSetDevice(tree->device));
+    CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     cudaEvent_t e0, e1;
     CT_CUDA(cudaEventCreate(&e0));

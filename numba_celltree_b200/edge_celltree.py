@@ -11,7 +11,7 @@ import numpy as np
 
 from numba_celltree_b200 import _lib
 from numba_celltree_b200.cast import cast_edges, cast_vertices
-from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _is_cuda_tensor, _ptr
+from numba_celltree_b200.celltree_base import CellTree2dBase, DeviceTree, _aligned, _is_cuda_tensor, _ptr
 from numba_celltree_b200.constants import MIN_TOLERANCE, TOLERANCE_FACTOR, FloatArray, IntArray, IntDType
 
 
@@ -69,18 +69,13 @@ class EdgeCellTree2d(CellTree2dBase):
         if _is_cuda_tensor(edge_coords):
             if edge_coords.dim() != 3 or tuple(edge_coords.shape[1:]) != (2, 2) or str(edge_coords.dtype) != "torch.float64":
                 raise ValueError("edges must have shape (n_edge, 2, 2)")
-            edge_coords = edge_coords.contiguous()
+            edge_coords = _aligned(edge_coords)
             device = edge_coords.device
         else:
             edge_coords = cast_edges(edge_coords)
-        handle = ctypes.c_void_p()
-        _lib.check(
-            _lib.load().ct_intersect_edges(
-                self._tree.handle, _ptr(edge_coords), edge_coords.shape[0],
-                _lib.CT_MEM_HOST if device is None else _lib.CT_MEM_DEVICE, ctypes.byref(handle),
-            )
-        )  # fmt: skip
-        i, j, xy = self._fetch(handle, payload_shape=(2, 2), device=device)
+        i, j, xy = self._variable(
+            "ct_intersect_edges", _ptr(edge_coords), edge_coords.shape[0], tensors=(edge_coords,), payload_shape=(2, 2), device=device
+        )
         if device is not None:
             return i, j, xy[:, 0].contiguous()
         return i, j, np.ascontiguousarray(xy[:, 0])
