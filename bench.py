@@ -42,8 +42,6 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "locate_points queries/s"
 UNIT = "queries/s"
-# 16 B point + 8 B result + 24 node visits x 32 B + 1.5 cells x (4 B index + 16 B face row + 64 B vertices)
-ALGORITHMIC_BYTES_PER_QUERY = 918.0
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -336,6 +334,317 @@ def run_reference(args):
     emit(line)
 
 
+def csrc_sha256() -> str:
+    """Hash of the kernel sources: ties a committed ncu capture (profiles/traffic.json) to the code that is running
+    (the GPU box has no .git, so a commit hash cannot be compared there)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted((ROOT / "numba_celltree_b200" / "csrc").glob("*.cu*")) + sorted((ROOT / "include").glob("*.h"))
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def device_ms(torch, fn, reps=3):
+    """Best device time of `fn` over `reps` runs (CUDA events on the current stream, which is the library's)."""
+    fn()
+    torch.cuda.synchronize()
+    best, result = None, None
+    for _ in range(reps):
+        result = None  # free the previous result first: the allocator then reuses its block
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        result = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return best, result
+
+
+def host_ms(torch, fn, reps=2):
+    """Best wall time of `fn` (NumPy in, NumPy out: the copies are inside)."""
+    fn()
+    best, result = None, None
+    for _ in range(reps):
+        result = None
+        t0 = time.perf_counter()
+        result = fn()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        best = ms if best is None else min(best, ms)
+    return best, result
+
+
+def traversal_roofline(lib, _lib, tree, dev_points, tolerance, n_points, nx, kernel_ms, order_ms, ms_per_step, peak, peak_source):
+    """The roofline object of the dominant kernel, from what that kernel as built has to move."""
+    import ctypes
+
+    m = int(tree._tree.info.n_max_vert)
+    sample = min(n_points, 4_000_000)
+    stats = (ctypes.c_int64 * 6)()
+    _lib.check(lib.ct_locate_points_stats(tree._tree.handle, dev_points.data_ptr(), sample, float(tolerance), stats))
+    slots, headers, cells, pushes, from_grid, found = (stats[k] / sample for k in range(6))
+    # per query: its 32-byte record, the entry-grid lookup (4-byte handle + the two 8-byte cell bounds), 16 bytes per node slot
+    # and per treelet header read, one row of elem_xy (16 bytes per vertex) per cell tested, the 8-byte (index, result) pair
+    bytes_per_query = 32.0 + 4.0 + 16.0 + 16.0 * slots + 16.0 * headers + cells * 16.0 * m + 8.0
+    achieved = bytes_per_query * n_points / (kernel_ms * 1e-3) / 1e9
+    info = tree._tree.info
+    tree_bytes = 128.0 * (int(info.n_nodes) / 3.5) + int(info.n_elem) * 16.0 * m  # treelets (about 3.5 nodes per line) + elem_xy
+    compulsory = 16.0 * n_points + 8.0 * n_points + tree_bytes  # points in, results out, tree once
+    l2 = ctypes.c_double()
+    hbm = ctypes.c_double()
+    _lib.check(lib.ct_measure_read_bandwidth(64 << 20, 40, ctypes.byref(l2)))
+    _lib.check(lib.ct_measure_read_bandwidth(4 << 30, 2, ctypes.byref(hbm)))
+    roofline = {
+        "bound": "hbm",
+        "kernel": "k_locate_points_binned<4,false,4,false> (tile sort + entry grid + treelet descent + point-in-polygon; one launch per step)",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_source,
+        "algorithmic_bytes_per_query": bytes_per_query,
+        "algorithmic_bytes_formula": "32 record + 4 entry handle + 16 entry bounds + 16*slots + 16*headers + cells*16*M + 8 result pair",
+        "per_query": {"node_slots": slots, "treelet_headers": headers, "cells_tested": cells, "stack_pushes": pushes,
+                      "started_from_entry_grid": from_grid, "found": found, "sample": sample},
+        "kernel_ms": kernel_ms,
+        "kernel_share_of_step": kernel_ms / ms_per_step,
+        "binning_ms": order_ms,
+        "results_to_caller_order_ms": ms_per_step - order_ms - kernel_ms,
+        "step_compulsory_hbm_bytes": compulsory,
+        "step_compulsory_frac": compulsory / (ms_per_step * 1e-3) / 1e9 / peak,
+        "measured_in_run": {"l2_read_gbs": l2.value, "hbm_read_gbs": hbm.value,
+                            "how": "ct_measure_read_bandwidth: 16-byte loads, 64 MB buffer x 40 sweeps (L2) and 4 GB x 2 sweeps (HBM)"},
+        "kernel_frac_of_l2": achieved / l2.value,
+    }  # fmt: skip
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists() and n_points == 100_000_000 and nx == 4096:
+        try:
+            t = json.loads(traffic_file.read_text())
+            if t.get("csrc_sha256") == csrc_sha256():
+                roofline["traffic"] = t["traversal_dram_bytes_per_launch"]
+                roofline["traffic_source"] = t.get("source")
+                roofline["dram_gbs"] = roofline["traffic"] / (kernel_ms * 1e-3) / 1e9
+                roofline["dram_frac"] = roofline["dram_gbs"] / peak
+                if t.get("traversal_l2_bytes_per_launch"):
+                    roofline["l2_gbs"] = t["traversal_l2_bytes_per_launch"] / (kernel_ms * 1e-3) / 1e9
+                    roofline["l2_frac"] = roofline["l2_gbs"] / l2.value
+                if t.get("step_dram_bytes"):
+                    roofline["step_dram_bytes"] = t["step_dram_bytes"]
+                    roofline["step_dram_over_compulsory"] = t["step_dram_bytes"] / compulsory
+            else:
+                roofline["traffic_note"] = "profiles/traffic.json was captured from other kernel sources (csrc_sha256 differs): dropped"
+        except Exception as e:  # noqa: BLE001
+            roofline["traffic_note"] = f"profiles/traffic.json unreadable: {e}"
+    roofline["note"] = (
+        "frac = bytes the traversal as built reads and writes per query (counted by an instrumented run of the same walk, "
+        "ct_locate_points_stats) x queries / launch time / HBM peak; after binning most node and polygon reads are L1/L2 hits, "
+        "so kernel_frac_of_l2 and dram_frac (ncu) say where the launch stands against either level"
+    )
+    return roofline
+
+
+def secondary_metrics(torch, tree_c2, dev_points, n_points, peak):
+    """Driver-run lines for the other BASELINE.json configurations (single GPU): device-resident and NumPy-to-NumPy times,
+    the figure of SURVEY 8(d)'s bytes-per-unit formula against the HBM peak."""
+    from numba_celltree_b200 import CellTree2d
+    from numba_celltree_b200.synthetic import c3_boxes, c4_edges, delaunay_mesh, quad_mesh
+
+    out = []
+
+    def line(config, call, units, unit, dev_ms, e2e_ms, bytes_per_unit, formula, extra=None):
+        entry = {
+            "config": config, "call": call, "units": units, "unit": unit,
+            "device_ms": dev_ms, "device_units_per_s": units / (dev_ms * 1e-3),
+            "e2e_ms": e2e_ms, "e2e_units_per_s": None if e2e_ms is None else units / (e2e_ms * 1e-3),
+            "roofline": {"bytes_per_unit": bytes_per_unit, "formula": formula, "achieved_gbs": bytes_per_unit * units / (dev_ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": bytes_per_unit * units / (dev_ms * 1e-3) / 1e9 / peak},
+        }  # fmt: skip
+        entry.update(extra or {})
+        out.append(entry)
+
+    # C2, second half: locate_points + Wachspress weights, device-resident
+    w_ms, w = device_ms(torch, lambda: tree_c2.compute_barycentric_weights(dev_points))
+    line("C2", "compute_barycentric_weights", n_points, "queries", w_ms, None, 32 + 4 + 16 + 16 * 3 + 1.5 * 64 + 8 + 32,
+         "the locate_points bytes + 8*M bytes of weights written per query", {"weights_row_sum_mean": float(w[1].sum().item()) / n_points})
+    del w
+
+    n_c3 = env_int("CELLTREE_BENCH_C3_POINTS", 1_000_000)
+    n_q = env_int("CELLTREE_BENCH_C3_QUERIES", 10_000_000)
+    nq5 = env_int("CELLTREE_BENCH_C5_NX", 1000)
+    try:
+        vertices, faces = delaunay_mesh(n_c3, seed=1234)
+    except Exception as e:  # scipy missing
+        return [{"unavailable": str(e)}]
+    tree = CellTree2d(vertices, faces, -1)
+    mesh = f"Delaunay({n_c3} points) = {len(faces)} triangles, depth {tree.depth}, build {tree.build_ms:.1f} ms"
+    boxes = c3_boxes(len(faces), n_q)
+    d_boxes = torch.from_numpy(boxes).cuda()
+    d_ms, r = device_ms(torch, lambda: tree.locate_boxes(d_boxes))
+    pairs = int(r[0].shape[0])
+    del r
+    h_ms, _ = host_ms(torch, lambda: tree.locate_boxes(boxes))
+    line("C3", "locate_boxes", n_q, "boxes", d_ms, h_ms, 7800.0, "2 passes x (32 + 32*V + 36*C) + 16*P with V=87.0, C=26.9, P=12.64 (SURVEY 8d)",
+         {"pairs": pairs, "device_pairs_per_s": pairs / (d_ms * 1e-3), "mesh": mesh})
+    d_ms, r = device_ms(torch, lambda: tree.intersect_boxes(d_boxes))
+    kept = int(r[0].shape[0])
+    del r
+    h_ms, _ = host_ms(torch, lambda: tree.intersect_boxes(boxes))
+    line("C3", "intersect_boxes", n_q, "boxes", d_ms, h_ms, 7800.0 + 116.0 * pairs / n_q, "locate_boxes + 116 B per shortlisted pair for the clip (SURVEY 8d)",
+         {"pairs": kept, "device_pairs_per_s": kept / (d_ms * 1e-3)})
+    del d_boxes, boxes
+    edges = c4_edges(len(faces), n_q)
+    d_edges = torch.from_numpy(edges).cuda()
+    d_ms, r = device_ms(torch, lambda: tree.intersect_edges(d_edges))
+    pairs = int(r[0].shape[0])
+    del r
+    h_ms, _ = host_ms(torch, lambda: tree.intersect_edges(edges))
+    line("C4", "intersect_edges", n_q, "segments", d_ms, h_ms, 11500.0, "2 x (32 + 32*V + 36*C + 60*C') + 48*P + sort, V=109.5, C=41.0, P=8.65 (SURVEY 8d)",
+         {"pairs": pairs, "device_pairs_per_s": pairs / (d_ms * 1e-3)})
+    del d_edges, edges
+    qv, qf = quad_mesh(nq5, nq5)
+    dqv, dqf = torch.from_numpy(qv).cuda(), torch.from_numpy(qf).cuda()
+    d_ms, r = device_ms(torch, lambda: tree.intersect_faces(dqv, dqf, -1))
+    di, dj = r[0].cpu().numpy(), r[1].cpu().numpy()
+    del r
+    h_ms, (i, j, a) = host_ms(torch, lambda: tree.intersect_faces(qv, qf, -1), reps=3)
+    pairs = len(i)
+    line("C5", "intersect_faces", pairs, "pairs", d_ms, h_ms, 7800.0 * len(qf) / max(pairs, 1) + 157.0 * 1.21 + 164.0,
+         "per final pair: the shortlist walk of its face (7.8 KB per face) + 157 B per SAT pair + 164 B per clipped pair (SURVEY 8d)",
+         {"metric": "intersect_faces pairs/s", "query_faces": len(qf), "sum_area": float(a.sum()),
+          "pairs_equal_host_path": bool(np.array_equal(di, i) and np.array_equal(dj, j)),
+          "workload": f"C5: {nq5}x{nq5} quads intersect_faces against {mesh}"})
+    return out
+
+
+def c1_reference_line():
+    """C1 of BASELINE.json: the reference itself on its own CPU-runnable case (generate_disk(25, 20) + 1 M points)."""
+    sys.path.insert(0, str(ROOT / "baseline"))
+    try:
+        import reference as ref_arm
+
+        ref, info = ref_arm.load_reference()
+    except Exception as e:  # noqa: BLE001
+        return {"config": "C1", "unavailable": f"{type(e).__name__}: {e}"}
+    from numba_celltree_b200.synthetic import c1_points, generate_disk
+
+    v, f = generate_disk(25, 20)
+    tree = ref.CellTree2d(v, f, -1)
+    pts = c1_points()
+    tree.locate_points(pts[:1000])
+    _, best, result = ref_arm.time_calls(lambda: tree.locate_points(pts), 3)
+    return {
+        "config": "C1", "call": "numba_celltree.CellTree2d.locate_points (reference, CPU)", "units": len(pts), "unit": "queries",
+        "queries_per_s": len(pts) / best, "cores": info["numba_threads"], "cells": len(f), "found_fraction": float((result >= 0).mean()),
+    }  # fmt: skip
+
+
+def multi_gpu_section(torch, dist, ctd, tree, device, rank, world, n_points, steps, tolerance):
+    """world > 1: strong scaling of the one C2 batch, the variable-length sharded calls on C3 / C5 with their one
+    collective, and a rank-0-versus-shards parity check."""
+    from numba_celltree_b200 import CellTree2d
+    from numba_celltree_b200.synthetic import c2_points, c3_boxes, delaunay_mesh, quad_mesh
+
+    def synced_ms(fn, reps):
+        fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        result = None
+        for _ in range(reps):
+            result = None
+            result = fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), result
+
+    # ---- strong scaling: the ONE batch of n_points seed-42 points, split by shard_range, results assembled on every GPU
+    lo, hi = ctd.shard_range(n_points, rank, world)
+    whole = c2_points(n_points)
+    mine = torch.from_numpy(whole[lo:hi]).to(device)
+    del whole
+    equal_shards = n_points % world == 0
+    assembled = torch.empty(n_points, dtype=torch.int64, device=device) if equal_shards else None
+
+    def strong_step():
+        found = tree.locate_points(mine)
+        if assembled is not None:
+            dist.all_gather_into_tensor(assembled, found)
+        return found
+
+    ms, found = synced_ms(strong_step, steps)
+    checksum = int(assembled.sum().item()) if assembled is not None else None
+    strong = {
+        "metric": METRIC, "scaling": "strong", "total_queries": n_points, "per_gpu_queries": hi - lo, "ms_per_step": ms,
+        "value": n_points / (ms * 1e-3), "unit": UNIT,
+        "assembled": "all_gather_into_tensor of the int64 results on every GPU (NCCL), inside the timed step" if equal_shards else "left sharded",
+        "result_checksum": checksum,
+    }  # fmt: skip
+    del mine, assembled, found
+
+    # ---- variable-length calls, sharded: C3 locate_boxes and C5 intersect_faces, exchange_totals inside the timed call
+    n_c3 = env_int("CELLTREE_BENCH_C3_POINTS", 1_000_000)
+    n_q = env_int("CELLTREE_BENCH_C3_QUERIES", 10_000_000)
+    nq5 = env_int("CELLTREE_BENCH_C5_NX", 1000)
+    c3 = None
+    n_tri = [0]
+    if rank == 0:
+        vertices, faces = delaunay_mesh(n_c3, seed=1234)
+        c3 = CellTree2d(vertices, faces, -1)
+        n_tri = [len(faces)]
+    dist.broadcast_object_list(n_tri, src=0)
+    c3 = ctd.broadcast_tree(c3, src=0, device=device)
+    boxes = c3_boxes(n_tri[0], n_q)
+    b_lo, b_hi = ctd.shard_range(n_q, rank, world)
+    d_boxes = torch.from_numpy(boxes).to(device)  # every rank holds the query set; it works on rows [lo, hi)
+    ms_boxes, pieces = synced_ms(lambda: ctd.query_pairs_sharded(c3, "locate_boxes", d_boxes, device=device), 3)
+    total_pairs = pieces[4]
+    qv, qf = quad_mesh(nq5, nq5)
+    dqv, dqf = torch.from_numpy(qv).to(device), torch.from_numpy(qf).to(device)
+    ms_faces, fpieces = synced_ms(lambda: ctd.intersect_faces_sharded(c3, dqv, dqf, -1, device=device), 3)
+    multi = {
+        "locate_boxes_sharded": {"config": "C3", "boxes": n_q, "pairs": int(total_pairs), "ms": ms_boxes, "boxes_per_s": n_q / (ms_boxes * 1e-3),
+                                 "pairs_per_s": total_pairs / (ms_boxes * 1e-3), "collective": "one all_gather_into_tensor of the per-rank pair counts"},
+        "intersect_faces_sharded": {"config": "C5", "faces": len(qf), "pairs": int(fpieces[4]), "ms": ms_faces,
+                                    "pairs_per_s": fpieces[4] / (ms_faces * 1e-3)},
+    }  # fmt: skip
+
+    # ---- parity: rank 0 alone versus the assembled shards (what tests/test_gpu_multi.py checks, run by the driver here)
+    n_par = 1_000_000
+    par_pts = torch.from_numpy(c2_points(n_par)).to(device)
+    p_lo, p_hi, part = ctd.locate_points_sharded(tree, par_pts)
+    equal = n_par % world == 0
+    gathered = torch.empty(n_par, dtype=torch.int64, device=device)
+    if equal:
+        dist.all_gather_into_tensor(gathered, part)
+    n_pb = 200_000
+    pb = ctd.query_pairs_sharded(c3, "intersect_boxes", d_boxes[:n_pb], device=device)
+    got = ctd.gather_pairs(*pb, dst=0)
+    fgot = ctd.gather_pairs(*fpieces, dst=0)
+    parity_multi = None
+    if rank == 0:
+        alone = tree.locate_points(par_pts)
+        wi, wj, wa = c3.intersect_boxes(d_boxes[:n_pb])
+        fi, fj, fa = c3.intersect_faces(dqv, dqf, -1)
+        parity_multi = {
+            "locate_points": {"queries": n_par, "bit_exact": bool(equal and torch.equal(alone, gathered))},
+            "intersect_boxes": {"boxes": n_pb, "pairs": int(wi.shape[0]),
+                                "bit_exact": bool(torch.equal(got[0], wi) and torch.equal(got[1], wj) and torch.equal(got[2], wa))},
+            "intersect_faces": {"pairs": int(fi.shape[0]),
+                                "bit_exact": bool(torch.equal(fgot[0], fi) and torch.equal(fgot[1], fj) and torch.equal(fgot[2], fa))},
+            "how": "rank 0 answers alone; the shards of all ranks are assembled on rank 0 (all_gather / point-to-point at the exchanged offsets)",
+        }  # fmt: skip
+    return strong, multi, parity_multi
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,11 +653,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-multi", action="store_true")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
+
+    import ctypes
 
     import torch
 
@@ -363,6 +675,7 @@ def main():
     device = torch.device("cuda", local_rank)
     lib = _lib.load()
     _lib.check(lib.ct_set_device(local_rank))
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
@@ -400,16 +713,12 @@ def main():
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
-
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
-        import torch.distributed as dist
-
         t = torch.tensor([x], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -435,10 +744,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * n_points / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel (the traversal, k_locate_points): CUDA events recorded by the library on the launching
-    # stream right around that launch; the Morton ordering (key kernel + radix sort passes) is timed separately.
-    import ctypes
-
+    # ---- dominant kernel (the traversal): CUDA events recorded by the library on the launching stream right around that
+    # launch; the binning before it is timed the same way, the rest of the step is the return of the results
     _lib.check(lib.ct_profile_enable(1))
     order_ms, kernel_ms = [], []
     for _ in range(min(args.steps, 5)):
@@ -448,64 +755,10 @@ def main():
         order_ms.append(a.value)
         kernel_ms.append(b.value)
     _lib.check(lib.ct_profile_enable(0))
-    kernel_avg_ms = float(np.mean(kernel_ms))
-    order_avg_ms = float(np.mean(order_ms))
     peak, peak_source = measured_peak()
-    achieved = ALGORITHMIC_BYTES_PER_QUERY * n_points / (kernel_avg_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm",
-        "kernel": "k_locate_points<4,false,9> (entry grid + treelet descent + point-in-polygon; one launch per step)",
-        "achieved": achieved,
-        "peak": peak,
-        "unit": "GB/s",
-        "frac": achieved / peak,
-        "traffic": None,
-        "peak_source": peak_source,
-        "algorithmic_bytes_per_query": ALGORITHMIC_BYTES_PER_QUERY,
-        "kernel_ms": kernel_avg_ms,
-        "kernel_share_of_step": kernel_avg_ms / ms_per_step,
-        "morton_order_ms": order_avg_ms,
-        "unpermute_ms": ms_per_step - order_avg_ms - kernel_avg_ms,
-        "step_achieved": ALGORITHMIC_BYTES_PER_QUERY * n_points / (ms_per_step * 1e-3) / 1e9,
-        "step_frac": ALGORITHMIC_BYTES_PER_QUERY * n_points / (ms_per_step * 1e-3) / 1e9 / peak,
-    }
-    traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists() and n_points == 100_000_000 and nx == 4096:
-        try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get("k_locate_points_bytes_per_launch")
-            roofline["traffic_source"] = "profiles/traffic.json (ncu --set full of this kernel on this workload)"
-            roofline["dram_gbs"] = roofline["traffic"] / (kernel_avg_ms * 1e-3) / 1e9
-            roofline["dram_frac"] = roofline["dram_gbs"] / peak
-        except Exception:
-            pass
-    roofline["note"] = (
-        "frac counts SURVEY 8d's algorithmic bytes (24 node visits x 32 B + cells + point + result per query); most of them "
-        "are served by L1/L2 after Morton ordering or skipped by the entry grid, so frac > 1 is not a DRAM rate -- dram_frac "
-        "(ncu DRAM bytes / launch time / peak) is; the kernel is issue- and latency-bound"
+    roofline = traversal_roofline(
+        lib, _lib, tree, dev_points, tolerance, n_points, nx, float(np.mean(kernel_ms)), float(np.mean(order_ms)), ms_per_step, peak, peak_source
     )
-
-    # ---- the other half of config C2: locate_points + barycentric (Wachspress) weights, device-resident ---------------------
-    weights_line = None
-    if rank == 0 and world == 1:
-        for _ in range(2):
-            tree.compute_barycentric_weights(dev_points)
-        torch.cuda.synchronize()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        w = None
-        for _ in range(3):
-            del w  # free the previous result first: the allocator then reuses its block instead of growing
-            _, w = tree.compute_barycentric_weights(dev_points)
-        w1.record()
-        torch.cuda.synchronize()
-        w_ms = w0.elapsed_time(w1) / 3
-        weights_line = {
-            "metric": "compute_barycentric_weights queries/s (device-resident)",
-            "value": n_points / (w_ms * 1e-3),
-            "ms_per_step": w_ms,
-            "weights_row_sum_mean": float(w.sum().item()) / n_points,
-        }
-        del w
 
     # ---- end to end through the public API with pinned host buffers --------------------------------------------------
     out_np = host_out.numpy()
@@ -527,7 +780,7 @@ def main():
     }
     same = bool(torch.equal(dev_out.cpu(), host_out))
 
-    # ---- CPU baseline + parity spot check (rank 0, single-GPU run only) ------------------------------------------------
+    # ---- CPU baseline + parity (rank 0, single-GPU run only) ------------------------------------------------
     cpu_baseline = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -551,11 +804,20 @@ def main():
             parity["reference_bit_exact"] = bool(np.array_equal(ref_result, out_np[:n_ref]))
             cpu_baseline["port_beside_it"] = port
         del cpu_result
+        tree.__dict__.pop("_mirrors", None)  # the 0.7 GB node mirror is not needed any more (nor its checksum per call)
 
-    # ---- second headline metric: intersect_faces pairs/s (C5), single GPU -----------------------------------------------
+    # ---- the other BASELINE.json configurations, single GPU --------------------------------------------------------
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
-        secondary = intersect_faces_metric(torch)
+        secondary = secondary_metrics(torch, tree, dev_points, n_points, peak)
+        if not args.no_cpu_baseline:
+            secondary.append(c1_reference_line())
+
+    # ---- multi-GPU: strong scaling, sharded variable-length calls, parity --------------------------------------------
+    strong = multi = parity_multi = None
+    if world > 1 and not args.no_multi:
+        del dev_points, dev_out
+        strong, multi, parity_multi = multi_gpu_section(torch, dist, ctd, tree, device, rank, world, n_points, min(args.steps, 5), tolerance)
 
     if rank == 0:
         line = {
@@ -575,13 +837,15 @@ def main():
                 "workload": name,
                 "per_gpu_queries": n_points,
                 "sharding": "tree replicated (NCCL broadcast), queries sharded by rank, no data-path collective",
-                "l2": "inputs larger than L2 (1.6 GB of points + 1.1 GB of tree per step vs 126 MB)",
+                "l2": "inputs larger than L2 (1.6 GB of points + 1.4 GB of tree per step vs 126 MB)",
                 "tree_build_ms": build_ms,
                 "tree_build_ms_first_call": build_ms_cold,
-                "queries_execution_order": "Morton (Z-order) over the tree bbox, radix sort inside the timed step",
+                "queries_execution_order": "points binned by a 16-bit Z-order key (count, offsets, scatter of 32-byte records), tiles of 2048 "
+                "sorted in shared memory; results returned through per-window queues; all inside the timed step",
                 "setup_s": round(setup_s, 2),
                 "tree_depth": tree.depth,
                 "tolerance": tolerance,
+                "csrc_sha256": csrc_sha256(),
             },
             "clocks": clocks,
             "e2e": e2e,
@@ -591,72 +855,13 @@ def main():
             "parity": parity,
             "e2e_equals_device_result": same,
             "secondary": secondary,
-            "barycentric_weights": weights_line,
+            "strong_scaling": strong,
+            "multi_gpu": multi,
+            "parity_multi": parity_multi,
         }
         emit(line)
     if world > 1:
-        import torch.distributed as dist
-
         dist.destroy_process_group()
-
-
-def intersect_faces_metric(torch):
-    """C5: 1000 x 1000 quads intersect_faces against the 2M-triangle Delaunay tree (pairs/s, end to end)."""
-    from numba_celltree_b200 import CellTree2d
-    from numba_celltree_b200.synthetic import delaunay_mesh, quad_mesh
-
-    n_pts = env_int("CELLTREE_BENCH_C3_POINTS", 1_000_000)
-    nq = env_int("CELLTREE_BENCH_C5_NX", 1000)
-    try:
-        vertices, faces = delaunay_mesh(n_pts, seed=1234)
-    except Exception as e:  # scipy missing
-        return {"unavailable": str(e)}
-    tree = CellTree2d(vertices, faces, -1)
-    qv, qf = quad_mesh(nq, nq)
-    tree.intersect_faces(qv, qf, -1)
-    torch.cuda.synchronize()
-    times = []
-    n_pairs = 0
-    area = 0.0
-    for _ in range(3):
-        t0 = time.perf_counter()
-        i, j, a = tree.intersect_faces(qv, qf, -1)
-        times.append(time.perf_counter() - t0)
-        n_pairs = len(i)
-        area = float(a.sum())
-    best = min(times)
-    # the same call with the query mesh already on the device and the pairs left there (what a regridding step that
-    # builds its sparse weights on the GPU sees): CUDA events on the current stream, which is the library's
-    dqv = torch.from_numpy(qv).cuda()
-    dqf = torch.from_numpy(qf).cuda()
-    tree.intersect_faces(dqv, dqf, -1)
-    torch.cuda.synchronize()
-    dev_ms = []
-    for _ in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        di, dj, da = tree.intersect_faces(dqv, dqf, -1)
-        e1.record()
-        torch.cuda.synchronize()
-        dev_ms.append(e0.elapsed_time(e1))
-    device_resident = {
-        "value": int(di.shape[0]) / (min(dev_ms) * 1e-3),
-        "unit": "pairs/s",
-        "ms": min(dev_ms),
-        "pairs_equal_host_path": bool(int(di.shape[0]) == n_pairs and np.array_equal(di.cpu().numpy(), i) and np.array_equal(dj.cpu().numpy(), j)),
-    }
-    return {
-        "metric": "intersect_faces pairs/s",
-        "device_resident": device_resident,
-        "value": n_pairs / best,
-        "unit": "pairs/s",
-        "pairs": n_pairs,
-        "seconds": best,
-        "sum_area": area,
-        "workload": f"C5: {nq}x{nq} quads intersect_faces against Delaunay({n_pts} pts) = {len(faces)} triangles; NumPy in, NumPy out",
-        "tree_build_ms": tree.build_ms,
-        "tree_depth": tree.depth,
-    }
 
 
 if __name__ == "__main__":

@@ -211,6 +211,13 @@ int ct_points_in_triangles(const double *points, const int64_t *face_indices, in
                            int32_t n_max_vert, const double *vertices, int64_t n_vertex, double tolerance, uint8_t *inside,
                            int32_t mem);
 int ct_profile_binning(const ct_tree *tree, const double *points, int64_t n, int32_t repeats, double *ms_per_run);
+/* Diagnostics behind bench.py's roofline line.  ct_locate_points_stats: what the point traversal touches, summed over the
+ * n queries (points on the device): stats[0] node slots read (16 B each), [1] treelet headers read (16 B), [2] cells
+ * tested, [3] siblings deferred to the stack, [4] queries started from the entry grid, [5] queries that found a cell.
+ * ct_measure_read_bandwidth: read rate of `repeats` sweeps over a buffer of `bytes` bytes (64 MB: the L2 rate; several
+ * GB: the HBM rate), GB/s. */
+int ct_locate_points_stats(const ct_tree *tree, const double *points, int64_t n, double tolerance, int64_t *stats);
+int ct_measure_read_bandwidth(size_t bytes, int32_t repeats, double *gb_per_s);
 
 #ifdef __cplusplus
 }

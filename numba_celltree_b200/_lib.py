@@ -92,6 +92,8 @@ _SIGNATURES = {
     "ct_points_in_polygon": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_i32, c_void_p, c_i32]),
     "ct_points_in_triangles": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_void_p, c_i64, c_f64, c_void_p, c_i32]),
     "ct_profile_binning": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, ctypes.POINTER(c_f64)]),
+    "ct_locate_points_stats": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_f64, ctypes.POINTER(c_i64)]),
+    "ct_measure_read_bandwidth": (ctypes.c_int, [ctypes.c_size_t, c_i32, ctypes.POINTER(c_f64)]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -241,14 +241,12 @@ static __global__ void __launch_bounds__(WINDOW_THREADS) k_windows_to_out(const 
 // The binned copy of a batch of points.
 struct PointBins {
     Scratch<PointRecord> records;
-    Scratch<uint32_t> cursor;  // N_BINS bin cursors, then the window cursors
-    int64_t n_windows = 0;
+    Scratch<uint32_t> cursor;  // N_BINS bin cursors
 
     int build(const ct_tree *tree, const double2 *points, int64_t n, cudaStream_t s) {
-        n_windows = (n + WINDOW - 1) >> WINDOW_BITS;
         CT_CHECK(records.alloc(n, s));
-        CT_CHECK(cursor.alloc(N_BINS * CT_CURSOR_STRIDE + n_windows, s));
-        CT_CUDA(cudaMemsetAsync(cursor.p, 0, (N_BINS * CT_CURSOR_STRIDE + n_windows) * sizeof(uint32_t), s));
+        CT_CHECK(cursor.alloc(N_BINS * CT_CURSOR_STRIDE, s));
+        CT_CUDA(cudaMemsetAsync(cursor.p, 0, (N_BINS * CT_CURSOR_STRIDE) * sizeof(uint32_t), s));
         const BinGrid g{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy};
         const int grid = grid_for(n, BIN_BLOCK * BIN_PER_THREAD);
         k_bin_count<<<grid, BIN_BLOCK, 0, s>>>(points, n, g, cursor.p);
@@ -263,7 +261,52 @@ struct PointBins {
         CT_LAUNCH_CHECK();
         return CT_OK;
     }
-    uint32_t *window_cursor() const { return cursor.p + N_BINS * CT_CURSOR_STRIDE; }
+};
+
+// The other way to the same execution order: (bin, index) pairs sorted by the 16-bit bin (two 8-bit passes of CUB's radix
+// sort on 2-byte keys), the points gathered by the traversal's tiles.
+static __global__ void __launch_bounds__(256) k_bin_keys(const double2 *__restrict__ points, int64_t n, BinGrid g, uint16_t *__restrict__ keys,
+                                                          uint32_t *__restrict__ index) {
+    const int64_t first = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    double2 p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = first + k * 256;
+        p[k] = i < n ? __ldcs(points + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = first + k * 256;
+        if (i < n) {
+            keys[i] = (uint16_t)(point_key24(g, p[k].x, p[k].y) >> FINE_BITS);
+            index[i] = (uint32_t)i;
+        }
+    }
+}
+
+struct BinSort {
+    Scratch<uint16_t> keys_a, keys_b;
+    Scratch<uint32_t> idx_a, idx_b;
+    Scratch<char> tmp;
+    const uint32_t *perm = nullptr;
+
+    int build(const BinGrid &g, const double2 *points, int64_t n, cudaStream_t s) {
+        CT_CHECK(keys_a.alloc(n, s));
+        CT_CHECK(keys_b.alloc(n, s));
+        CT_CHECK(idx_a.alloc(n, s));
+        CT_CHECK(idx_b.alloc(n, s));
+        k_bin_keys<<<grid_for(n, 1024), 256, 0, s>>>(points, n, g, keys_a.p, idx_a.p);
+        CT_LAUNCH_CHECK();
+        cub::DoubleBuffer<uint16_t> d_keys(keys_a.p, keys_b.p);
+        cub::DoubleBuffer<uint32_t> d_vals(idx_a.p, idx_b.p);
+        size_t bytes = 0;
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_keys, d_vals, n, 0, BIN_BITS, s));
+        CT_CHECK(tmp.alloc(bytes, s));
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys, d_vals, n, 0, BIN_BITS, s));
+        count_launch(3);
+        perm = d_vals.Current();
+        return CT_OK;
+    }
 };
 
 }  // namespace ct

@@ -9,7 +9,7 @@ namespace ct {
 // count -> scan -> fill: the traversal runs twice.  The candidate test is four comparisons, so a second traversal is
 // cheaper than logging the hits of the first (measured on C3: 14.2 ms against 16.5 ms with the hit log that
 // intersect_edges uses, whose candidate test is a clip).
-template <bool FILL>
+template <bool FILL, bool DEEP>
 __global__ void __launch_bounds__(BLOCK) k_locate_boxes(TreeView t, const double *__restrict__ boxes, int64_t n,
                                                         int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
                                                         int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
@@ -20,12 +20,12 @@ __global__ void __launch_bounds__(BLOCK) k_locate_boxes(TreeView t, const double
     Box4 box = load_box(boxes, q);
     if constexpr (FILL) {
         int64_t base = offsets[q];
-        locate_box(t, box, [&](int k, int bbox_index) {
+        locate_box<DEEP>(t, box, [&](int k, int bbox_index) {
             out_i[base + k] = (int32_t)q;
             out_j[base + k] = bbox_index;
         });
     } else {
-        counts[q] = locate_box(t, box, [](int, int) {});
+        counts[q] = locate_box<DEEP>(t, box, [](int, int) {});
     }
 }
 
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(BLOCK) k_box_area(TreeView t, const double *__
     Poly<4> a;
     box_polygon(load_box(boxes, pi[k]), a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
+    load_tree_polygon<MAXB>(t, pj[k], b);
     double ar = clip_area_of_pair<4, MAXB, BLOCK>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(BLOCK) k_sat(TreeView t, const int32_t *__rest
     Poly<MAXA> a;
     gather_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
+    load_tree_polygon<MAXB>(t, pj[k], b);
     flag[k] = (separating_axes<MAXA, MAXB>(a, b) && separating_axes<MAXB, MAXA>(b, a)) ? 1 : 0;
 }
 
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip_area(TreeView t, const int32_t *
     Poly<MAXA> a;
     gather_polygon<MAXA>(qfaces, qM, pi[k], qvertices, a);
     Poly<MAXB> b;
-    load_polygon<MAXB>(t.elements, t.M, pj[k], t.elem_xy, b);
+    load_tree_polygon<MAXB>(t, pj[k], b);
     double ar = clip_area_of_pair<MAXA, MAXB, BLOCK>(a, b);
     area[k] = ar;
     flag[k] = ar > 0 ? 1 : 0;
@@ -96,8 +96,13 @@ static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64
     int64_t total = 0;
     MortonOrder order;
     CT_CHECK(order.build<KEY_BOX>(tree, d_boxes, n, s));
+    DeepScope deep;
+    CT_CHECK(deep.init(tree, n, s));
+    v.deep = deep.view;
     if (n > 0) {
-        k_locate_boxes<false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr, order.perm);
+        CT_CHECK(deep.next_launch());
+        if (deep.view.slab) k_locate_boxes<false, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr, order.perm);
+        else k_locate_boxes<false, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, counts.p, nullptr, nullptr, nullptr, order.perm);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -106,11 +111,13 @@ static int locate_boxes_device(const ct_tree *tree, const double *d_boxes, int64
     r->size = total;
     r->width = 0;
     if (n > 0 && total > 0) {
-        k_locate_boxes<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j, order.perm);
+        CT_CHECK(deep.next_launch());
+        if (deep.view.slab) k_locate_boxes<true, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j, order.perm);
+        else k_locate_boxes<true, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_boxes, n, nullptr, offsets.p, r->i, r->j, order.perm);
         CT_LAUNCH_CHECK();
     }
     trace_point(s, "boxes: count/scan/fill");
-    return CT_OK;
+    return deep.finish();
 }
 
 template <int MAXB>
@@ -164,7 +171,6 @@ extern "C" int ct_locate_boxes(const ct_tree *tree, const double *boxes, int64_t
         set_error("ct_locate_boxes: areas need a face tree");
         return CT_ERR_VALUE;
     }
-    CT_CHECK(check_depth(tree));
     CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     DevIn<double> d_boxes;
@@ -222,7 +228,6 @@ extern "C" int ct_locate_faces(const ct_tree *tree, const double *vertices, int6
         set_error("ct_locate_faces: faces must have 3..32 columns");
         return CT_ERR_VALUE;
     }
-    CT_CHECK(check_depth(tree));
     CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     const int qM = n_max_vert;

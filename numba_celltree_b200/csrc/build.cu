@@ -737,11 +737,17 @@ __global__ void __launch_bounds__(BB) k_emit_nodes(BuildState st, const int32_t 
 // ---- query-side acceleration data derived from the finished tree -----------------------------------------
 // elem_xy: vertex coordinates per element row (see geometry.cuh: load_polygon)
 __global__ void __launch_bounds__(BB) k_elem_coords(const double2 *__restrict__ vertices, const int32_t *__restrict__ elements,
-                                                    int64_t count, double2 *__restrict__ xy) {
+                                                    int64_t count, double2 *__restrict__ xy, int32_t *__restrict__ collision) {
     int64_t k = (int64_t)blockIdx.x * BB + threadIdx.x;
     if (k >= count) return;
     int v = elements[k];
-    xy[k] = v >= 0 ? vertices[v] : make_double2(0.0, 0.0);
+    const double pad = __longlong_as_double((long long)PAD_VERTEX_BITS);
+    double2 c = make_double2(pad, pad);
+    if (v >= 0) {
+        c = vertices[v];
+        if ((unsigned long long)__double_as_longlong(c.x) == PAD_VERTEX_BITS) *collision = 1;  // a real vertex looks like padding
+    }
+    xy[k] = c;
 }
 
 // ---- treelets (common.cuh): three binary levels per 128-byte line -------------------------------------------------
@@ -970,8 +976,17 @@ static int build_entry_grid(ct_tree *tree, cudaStream_t s) {
 static int finish_query_data(ct_tree *tree, cudaStream_t s) {
     const int64_t count = tree->n_elem * tree->M;
     CT_CHECK(dalloc(&tree->elem_xy, (size_t)(count > 0 ? count : 1), s));
-    k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy);
-    CT_LAUNCH_CHECK();
+    {
+        Scratch<int32_t> collision;
+        CT_CHECK(collision.alloc(1, s));
+        CT_CUDA(cudaMemsetAsync(collision.p, 0, sizeof(int32_t), s));
+        k_elem_coords<<<grid_for(count, BB), BB, 0, s>>>(tree->vertices, tree->elements, count, tree->elem_xy, collision.p);
+        CT_LAUNCH_CHECK();
+        int32_t h = 0;
+        CT_CUDA(cudaMemcpyAsync(&h, collision.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaStreamSynchronize(s));
+        tree->length_from_rows = h != 0;
+    }
     CT_CHECK(build_treelets(tree, s));
     CT_CHECK(build_entry_grid(tree, s));
     return CT_OK;

@@ -71,6 +71,15 @@ __device__ __forceinline__ uint32_t grid_coord(double v, double vmin, double sca
     return f < 65535.0 ? (uint32_t)f : 65535u;
 }
 
+// Overflow area of the traversal stacks (traverse.cuh: Stack) for trees deeper than the per-thread part: `slots`
+// columns of (depth - STACK_CAP) entries, entry k of column c at slab[k * slots + c]; a thread takes a column the first
+// time its stack outgrows the per-thread part.  All null for trees that fit (every tree the builder makes of a sane mesh).
+struct DeepStacks {
+    uint32_t *slab;
+    int32_t *state;  // [0] columns handed out, [1] set when a thread found none left
+    int32_t slots;
+};
+
 struct TreeView {  // passed by value to kernels
     const Node32 *nodes;
     const int32_t *bb_indices;
@@ -83,11 +92,17 @@ struct TreeView {  // passed by value to kernels
     // per-element vertex coordinates, (n_elem, M) double2: the polygon of element e is read with one contiguous
     // access instead of a face row followed by M dependent vertex gathers
     const double2 *elem_xy;
+    // padding of elem_xy rows is PAD_VERTEX (a NaN with a payload of its own), so the length of a polygon of up to four
+    // vertices is read off its coordinates; true only if a real vertex carries that very bit pattern: then the id row decides
+    bool length_from_rows;
     const Treelet *treelets;
     EntryGrid entry;
+    DeepStacks deep;
 };
 
 constexpr int MAX_N_VERTEX = 32;      // constants.py:128
+// coordinate of the padding vertices of elem_xy: a quiet NaN whose payload no computation produces
+constexpr unsigned long long PAD_VERTEX_BITS = 0x7ff8c0dec0dec0deULL;
 constexpr double MIN_TOLERANCE = 1e-15;   // constants.py:140
 constexpr double TOLERANCE_FACTOR = 1e-12;  // constants.py:141
 constexpr double FLOAT_MAX = 1.7976931348623157e308;   // constants.py:144
@@ -246,7 +261,17 @@ struct DevOut {
 };
 
 
-int check_depth(const ct_tree *tree);
+// Host side of DeepStacks: nothing for trees of at most STACK_CAP levels.  `threads` bounds how many threads of one
+// launch can need a column at the same time.
+struct DeepScope {
+    Scratch<uint32_t> slab;
+    Scratch<int32_t> state;
+    DeepStacks view{nullptr, nullptr, 0};
+    cudaStream_t stream = 0;
+    int init(const ct_tree *tree, int64_t threads, cudaStream_t s);
+    int next_launch();  // before every launch that walks the tree: all columns are free again
+    int finish();       // after the last one: CT_ERR_DEPTH if a thread found no column
+};
 // phase events of the last ct_locate_points call (lib.cu); nullptr when profiling is off
 struct PhaseEvents {
     cudaEvent_t start, ordered, done;
@@ -278,6 +303,7 @@ struct ct_tree {
     int32_t *elements = nullptr;
     double2 *vertices = nullptr;
     double2 *elem_xy = nullptr;
+    bool length_from_rows = false;
     ct::Treelet *treelets = nullptr;
     int64_t n_treelets = 0;
     uint32_t *entry_handle = nullptr;
@@ -296,6 +322,7 @@ struct ct_tree {
         v.n_elem = (int32_t)n_elem;
         for (int k = 0; k < 4; k++) v.bbox[k] = bbox[k];
         v.elem_xy = elem_xy;
+        v.length_from_rows = length_from_rows;
         v.treelets = treelets;
         v.entry.handle = entry_handle;
         v.entry.lo = entry_lo;
@@ -304,6 +331,9 @@ struct ct_tree {
         v.entry.ymin = bbox[2];
         v.entry.sx = grid_sx;
         v.entry.sy = grid_sy;
+        v.deep.slab = nullptr;
+        v.deep.state = nullptr;
+        v.deep.slots = 0;
         return v;
     }
 };

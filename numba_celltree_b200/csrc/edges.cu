@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     }
     const P2 V = to_vector(a, b);
     const char *base = reinterpret_cast<const char *>(t.treelets);
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
+    StackT<false> stack;  // deep trees take the per-thread count / fill kernels instead (run_edges)
     Cursor cur;
     cursor_enter(cur, base, ROOT_HANDLE);
     int leaf_k = 0;    // cells of the current leaf already pushed
@@ -101,16 +100,16 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
                 edge_plane_test(cur, a, b, V, left, right);
                 uint32_t left_handle, right_handle;
                 cursor_children(cur, left_handle, right_handle);
-                if (left && right) stack[sp++] = left_handle;
+                if (left && right) stack.push(t, left_handle);
                 next = right ? right_handle : left_handle;
                 pop = !(left || right);
             }
             if (pop) {
-                if (sp == 0) {
+                if (stack.empty()) {
                     active = false;
                     move = false;
                 } else {
-                    next = stack[--sp];
+                    next = stack.pop(t);
                 }
             }
             if (move) cursor_enter(cur, base, next);
@@ -247,7 +246,19 @@ __global__ void __launch_bounds__(256) k_rank_and_move(HitLog log, const double 
 }
 
 // the second traversal, one thread per segment: pairs in emission order (their ordinal is their rank)
+// first pass for trees deeper than the per-thread stack: one thread per segment counts its hits (no log)
 template <int MAXV>
+__global__ void __launch_bounds__(BLOCK) k_locate_edges_count_deep(TreeView t, const double *__restrict__ edges, int64_t n,
+                                                                   int32_t *__restrict__ counts, const uint32_t *__restrict__ perm) {
+    int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (q >= n) return;
+    if (perm) q = __ldg(perm + q);
+    const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
+    double2 a2 = __ldg(e), b2 = __ldg(e + 1);
+    counts[q] = locate_edge<MAXV, true>(t, P2{a2.x, a2.y}, P2{b2.x, b2.y}, [](int, int, P2, P2) {});
+}
+
+template <int MAXV, bool DEEP>
 __global__ void __launch_bounds__(BLOCK) k_locate_edges_fill(TreeView t, const double *__restrict__ edges, int64_t n,
                                                              const int64_t *__restrict__ offsets, int32_t *__restrict__ out_i,
                                                              int32_t *__restrict__ out_j, double *__restrict__ out_xy,
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(BLOCK) k_locate_edges_fill(TreeView t, const d
     double2 a2 = __ldg(e), b2 = __ldg(e + 1);
     P2 a{a2.x, a2.y}, b{b2.x, b2.y};
     const int64_t base = offsets[q];
-    locate_edge<MAXV>(t, a, b, [&](int k, int bbox_index, P2 c, P2 d) {
+    locate_edge<MAXV, DEEP>(t, a, b, [&](int k, int bbox_index, P2 c, P2 d) {
         out_i[base + k] = (int32_t)q;
         out_j[base + k] = bbox_index;
         ordinal[base + k] = k;
@@ -333,8 +344,14 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     HitLogBuffers buffers;
     CT_CHECK(buffers.alloc(n, hit_log_per_query(), true, s));
     const HitLog &log = buffers.log;
+    DeepScope deep;
+    CT_CHECK(deep.init(tree, n, s));
+    v.deep = deep.view;
+    const bool deep_tree = deep.view.slab != nullptr;
     if (n > 0) {
-        k_edges_cooperative<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
+        CT_CHECK(deep.next_launch());
+        if (deep_tree) k_locate_edges_count_deep<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm);
+        else k_edges_cooperative<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm, log);
         CT_LAUNCH_CHECK();
     }
     CT_CHECK(scan_counts(counts.p, n, offsets.p, &total, s));
@@ -344,7 +361,7 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     r->size = total;
     r->width = 4;
     if (n > 0 && total > 0) {
-        if (total <= log.capacity) {
+        if (!deep_tree && total <= log.capacity) {
             // every hit is in the log: note where (one slot per hit in its segment's range), then rank and move
             Scratch<uint32_t> source;
             CT_CHECK(source.alloc(total, s));
@@ -357,15 +374,20 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
             // the log overflowed: second traversal, pairs in emission order, then the per-segment insertion sort
             Scratch<int32_t> ordinal;
             CT_CHECK(ordinal.alloc(total, s));
-            k_locate_edges_fill<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
-                                                                          ordinal.p, order.perm);
+            CT_CHECK(deep.next_launch());
+            if (deep_tree)
+                k_locate_edges_fill<MAXV, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
+                                                                                    ordinal.p, order.perm);
+            else
+                k_locate_edges_fill<MAXV, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
+                                                                                     ordinal.p, order.perm);
             CT_LAUNCH_CHECK();
             k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload, ordinal.p);
             CT_LAUNCH_CHECK();
         }
     }
     CT_CUDA(cudaStreamSynchronize(s));
-    return CT_OK;
+    return deep.finish();
 }
 }  // namespace ct
 
@@ -381,7 +403,6 @@ extern "C" int ct_intersect_edges(const ct_tree *tree, const double *edges, int6
         set_error("ct_intersect_edges: null argument");
         return CT_ERR_VALUE;
     }
-    CT_CHECK(check_depth(tree));
     CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     DevIn<double> d_edges;

@@ -99,6 +99,34 @@ CT_DEV void load_polygon(const int32_t *__restrict__ elements, int M, int64_t el
     }
 }
 
+// A cell of the tree.  Rows of up to four vertices: the coordinates alone are read (one contiguous access); a fourth
+// vertex that is the padding marker means a triangle in a quad row (polygon_length, geometry_utils.py:72-79, scans the
+// id row for the first -1 from column 3 on -- the marker sits exactly where the id row holds -1).
+template <int MAXV>
+CT_DEV void load_tree_polygon(const TreeView &t, int64_t elem, Poly<MAXV> &poly) {
+    if constexpr (MAXV <= 4) {
+        if (!t.length_from_rows) {
+            const int M = t.M;
+            const double2 *c = t.elem_xy + elem * (int64_t)M;
+            double2 v[MAXV];
+#pragma unroll
+            for (int k = 0; k < MAXV; k++) v[k] = (k < M) ? __ldg(c + k) : make_double2(0.0, 0.0);
+            int n = M < MAXV ? M : MAXV;
+            if constexpr (MAXV == 4) {
+                if (M == 4 && (unsigned long long)__double_as_longlong(v[3].x) == PAD_VERTEX_BITS) n = 3;
+            }
+            poly.n = n;
+#pragma unroll
+            for (int k = 0; k < MAXV; k++) {
+                poly.x[k] = v[k].x;
+                poly.y[k] = v[k].y;
+            }
+            return;
+        }
+    }
+    load_polygon<MAXV>(t.elements, t.M, elem, t.elem_xy, poly);
+}
+
 // The same for a polygon given by vertex ids into a vertex array (query faces of ct_locate_faces).
 template <int MAXV>
 CT_DEV void gather_polygon(const int32_t *__restrict__ elements, int M, int64_t elem, const double2 *__restrict__ vertices,

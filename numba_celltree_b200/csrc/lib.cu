@@ -65,10 +65,43 @@ int sort_bits_override() {
     return g_sort_bits;
 }
 
-int check_depth(const ct_tree *tree) {
-    if (tree->depth > STACK_CAP) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "tree has %d levels; the traversal stack holds %d", tree->depth, STACK_CAP);
+// ---- overflow slab of the traversal stacks (common.cuh: DeepStacks, traverse.cuh: Stack) ------------------------------
+int DeepScope::init(const ct_tree *tree, int64_t threads, cudaStream_t s) {
+    stream = s;
+    const int64_t extra = (int64_t)tree->depth - STACK_CAP;
+    if (extra <= 0 || threads <= 0) return CT_OK;
+    // a column per thread of the launch if that fits the budget, else as many as fit: only threads whose stack really
+    // holds more than STACK_CAP deferred siblings take one, and that takes a query crossing that many overlapping nodes
+    static int64_t budget = -1;
+    if (budget < 0) {
+        const char *e = getenv("CELLTREE_DEEP_STACK_MB");
+        budget = (e ? atoll(e) : 2048) << 20;
+    }
+    int64_t slots = budget / (4 * extra);
+    if (slots > threads) slots = threads;
+    if (slots < 1) slots = 1;
+    if (slots > INT32_MAX) slots = INT32_MAX;
+    CT_CHECK(slab.alloc((size_t)slots * extra, s));
+    CT_CHECK(state.alloc(2, s));
+    CT_CUDA(cudaMemsetAsync(state.p, 0, 2 * sizeof(int32_t), s));
+    view.slab = slab.p;
+    view.state = state.p;
+    view.slots = (int32_t)slots;
+    return CT_OK;
+}
+int DeepScope::next_launch() {
+    if (view.state) CT_CUDA(cudaMemsetAsync(view.state, 0, sizeof(int32_t), stream));
+    return CT_OK;
+}
+int DeepScope::finish() {
+    if (!view.state) return CT_OK;
+    int32_t h[2] = {0, 0};
+    CT_CUDA(cudaMemcpyAsync(h, view.state, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CT_CUDA(cudaStreamSynchronize(stream));
+    if (h[1]) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "more than %d queries of one call needed a traversal stack deeper than %d entries at the same "
+                 "time: pass fewer queries per call or raise CELLTREE_DEEP_STACK_MB", view.slots, STACK_CAP);
         set_error(buf);
         return CT_ERR_DEPTH;
     }

@@ -25,7 +25,7 @@ template <int MAXV, bool WEIGHTS>
 CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, double *__restrict__ w_out) {
     const int M = t.M;
     Poly<MAXV> poly;  // the hit face again (its lines are in L1 from the test a moment ago)
-    if (found != -1) load_polygon<MAXV>(t.elements, M, found, t.elem_xy, poly);
+    if (found != -1) load_tree_polygon<MAXV>(t, found, poly);
     if constexpr (MAXV == 3) {
         // barycentric_triangle_weights, algorithms/barycentric_triangle.py:46-64
         double u = 0.0, v = 0.0, w = 0.0;
@@ -54,11 +54,12 @@ CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, 
     }
 }
 
-template <int MAXV, bool WEIGHTS, int MINB>
+template <int MAXV, bool WEIGHTS, int MINB, bool DEEP>
 __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                          double tolerance, int64_t *__restrict__ out,
                                                          double *__restrict__ weights, const uint32_t *__restrict__ perm,
-                                                         int32_t *__restrict__ out_in_order) {
+                                                         int32_t *__restrict__ out_in_order, uint2 *__restrict__ pairs = nullptr,
+                                                         uint32_t *__restrict__ window_cursor = nullptr) {
     __shared__ double2 s_points[PER_THREAD * BLOCK];
     __shared__ uint32_t s_index[PER_THREAD * BLOCK];
     const int64_t first = (int64_t)blockIdx.x * (PER_THREAD * BLOCK) + threadIdx.x;
@@ -85,13 +86,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_locate_points(TreeView t, const
         const int64_t i = perm ? (int64_t)s_index[k * BLOCK + threadIdx.x] : slot;
         const double2 pt = s_points[k * BLOCK + threadIdx.x];
         const P2 p{pt.x, pt.y};
-        const int found = locate_point<MAXV>(t, p, tolerance);
-        if (out_in_order) out_in_order[slot] = found;  // coalesced; MortonOrder::scatter_results puts it in place
+        uint32_t queue_slot = 0;
+        if (pairs) queue_slot = atomicAdd(window_cursor + ((uint32_t)i >> WINDOW_BITS), 1u);
+        const int found = locate_point<MAXV, NoProbe, DEEP>(t, p, tolerance);
+        if (pairs) pairs[((int64_t)((uint32_t)i >> WINDOW_BITS) << WINDOW_BITS) + queue_slot] = make_uint2((uint32_t)i, (uint32_t)found);
+        else if (out_in_order) out_in_order[slot] = found;  // coalesced; MortonOrder::scatter_results puts it in place
         else __stcs(out + i, (int64_t)found);
         if constexpr (WEIGHTS) write_weights<MAXV, WEIGHTS>(t, found, p, tolerance, weights + i * (int64_t)t.M);
     }
 }
 
+template <bool DEEP>
 __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, const double2 *__restrict__ points, int64_t n,
                                                                  double tolerance, int64_t *__restrict__ out,
                                                                  const uint32_t *__restrict__ perm, int32_t *__restrict__ out_in_order) {
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
     if (slot >= n) return;
     const int64_t i = perm ? (int64_t)__ldcs(perm + slot) : slot;
     double2 pt = __ldcs(points + i);
-    const int found = locate_point_on_edge(t, P2{pt.x, pt.y}, tolerance);
+    const int found = locate_point_on_edge<DEEP>(t, P2{pt.x, pt.y}, tolerance);
     if (out_in_order) out_in_order[slot] = found;
     else __stcs(out + i, (int64_t)found);
 }
@@ -121,53 +126,107 @@ constexpr int TILE = TILE_THREADS * TILE_ITEMS;
 using TileSort = cub::BlockRadixSort<uint16_t, TILE_THREADS, TILE_ITEMS, uint16_t>;
 struct TileShared {
     typename TileSort::TempStorage sort;
-    uint32_t span, key0;
+    uint32_t lo, hi;
 };
 
-template <int MAXV, bool WEIGHTS, int MINB>
+// Where a tile's queries come from: binned records (binning.cuh), or a permutation (sorted by the 16-bit bin) over the
+// caller's point array, gathered here.
+struct TileInput {
+    const PointRecord *records;  // binned records, or nullptr
+    const uint32_t *perm;        // else: query indices in bin order ...
+    const double2 *points;       // ... into the caller's points
+    BinGrid grid;
+};
+
+CT_DEV double2 load_point_once(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <int MAXV, bool WEIGHTS, int MINB, bool GATHER>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
-    k_locate_points_binned(TreeView t, const PointRecord *__restrict__ records, int64_t n, double tolerance,
-                           uint2 *__restrict__ pairs, uint32_t *__restrict__ window_cursor, int64_t *__restrict__ out,
-                           double *__restrict__ weights) {
+    k_locate_points_binned(TreeView t, TileInput in, int64_t n, double tolerance, uint2 *__restrict__ pairs,
+                           uint32_t *__restrict__ window_cursor, int64_t *__restrict__ out, double *__restrict__ weights) {
     __shared__ TileShared sh;
     const int64_t base = (int64_t)blockIdx.x * TILE;
     const int m = (int)((n - base) < TILE ? (n - base) : TILE);
-    const PointRecord *tile = records + base;
+    const PointRecord *tile = in.records + base;
+    const uint32_t *tile_perm = in.perm + base;
     if (threadIdx.x == 0) {
-        sh.span = 0;
-        // the records are in bin order, so no key of the tile is below its first record's bin
-        sh.key0 = (__ldg(&tile[0].key) >> FINE_BITS) << FINE_BITS;
+        sh.lo = 0xffffffffu;
+        sh.hi = 0;
     }
     __syncthreads();
-    // Only the keys are read for the sort (the records stay in L2 for the second read below): key relative to the
-    // tile's first bin, saturating.  Which thread holds which item does not matter to a sort; `source` says where
-    // the item sits in the tile.
-    const uint32_t key0 = sh.key0;
+    // Only the keys are needed for the sort (the records / points stay in L2 for the second read below).  Which thread
+    // holds which item does not matter to a sort; `source` says where the item sits in the tile.
+    uint32_t key24[TILE_ITEMS];
+    uint32_t lo = 0xffffffffu, hi = 0;
+    if constexpr (GATHER) {
+        uint32_t index[TILE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            index[k] = j < m ? __ldg(tile_perm + j) : 0u;
+        }
+        double2 pt[TILE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            if (j < m) pt[k] = load_point_once(in.points + index[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            key24[k] = j < m ? point_key24(in.grid, pt[k].x, pt[k].y) : 0xffffffffu;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            key24[k] = j < m ? __ldg(&tile[j].key) : 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TILE_ITEMS; k++) {
+        const int j = k * TILE_THREADS + threadIdx.x;
+        if (j < m) {
+            lo = key24[k] < lo ? key24[k] : lo;
+            hi = key24[k] > hi ? key24[k] : hi;
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&sh.lo, lo);
+        atomicMax(&sh.hi, hi);
+    }
+    __syncthreads();
+    // key relative to the tile's first bin, saturating (a tile that spans more than 256 bins is too sparse for the
+    // order of its far end to matter)
+    const uint32_t key0 = (sh.lo >> FINE_BITS) << FINE_BITS;
+    uint32_t span = sh.hi - key0;
+    span = span < 0xffffu ? span : 0xffffu;
     uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
-    uint32_t span = 0;
 #pragma unroll
     for (int k = 0; k < TILE_ITEMS; k++) {
         const int j = k * TILE_THREADS + threadIdx.x;
         uint32_t rel = 0xffffu;
         if (j < m) {
-            rel = __ldg(&tile[j].key) - key0;
+            rel = key24[k] - key0;
             rel = rel < 0xffffu ? rel : 0xffffu;
-            span = rel > span ? rel : span;
         }
         keys[k] = (uint16_t)rel;
         source[k] = (uint16_t)j;
     }
-    span = __reduce_max_sync(0xffffffffu, span);
-    if ((threadIdx.x & 31) == 0) atomicMax(&sh.span, span);
-    __syncthreads();
 #if CT_EXP2 == 2
     const int bits = 0;
 #else
-    const int bits = 32 - __clz(sh.span | 1u);
+    const int bits = 32 - __clz(span | 1u);
 #endif
     TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, bits);
     // thread t now holds the sorted positions t, t + 256, ...: a warp's 32 points are neighbours on the Z-order curve.
-    // The record of the next position is requested while the tree is walked for the current one, and so is the
+    // The point of the next position is requested while the tree is walked for the current one, and so is the
     // slot in the result queue of the query's window (an atomic whose answer is only needed after the walk).
     uint64_t order_lo = 0, order_hi = 0;  // source[] packed, so that the loop below can stay rolled without a local array
 #pragma unroll
@@ -176,10 +235,20 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         else order_hi |= (uint64_t)source[k] << (16 * (k - 4));
     }
     static_assert(TILE_ITEMS == 8, "source[] is packed into two 64-bit words");
-    double x, y;
-    uint32_t index, key;
+    double x = 0.0, y = 0.0;
+    uint32_t index = 0;
+    auto fetch = [&](int j) {
+        if constexpr (GATHER) {
+            index = __ldg(tile_perm + j);
+            const double2 pt = load_point_once(in.points + index);
+            x = pt.x, y = pt.y;
+        } else {
+            uint32_t key;
+            load_record(tile + j, x, y, index, key);
+        }
+    };
     int j = (int)(order_lo & 0xffffu);
-    if (j < m) load_record(tile + j, x, y, index, key);
+    if (j < m) fetch(j);
 #pragma unroll 1
     for (int k = 0; k < TILE_ITEMS; k++) {
         const bool valid = j < m;
@@ -187,7 +256,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         const uint32_t my_index = index;
         if (k + 1 < TILE_ITEMS) {
             j = (int)(((k + 1 < 4 ? order_lo : order_hi) >> (16 * ((k + 1) & 3))) & 0xffffu);
-            if (j < m) load_record(tile + j, x, y, index, key);
+            if (j < m) fetch(j);
         }
         if (!valid) continue;
         uint32_t slot = 0;
@@ -209,35 +278,40 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
 }
 
 template <int MAXV>
-static int launch_locate_points_binned(const TreeView &v, const PointRecord *records, int64_t n, double tol, uint2 *pairs,
+static int launch_locate_points_binned(const TreeView &v, const TileInput &in, int64_t n, double tol, uint2 *pairs,
                                        uint32_t *window_cursor, int64_t *out, double *weights, cudaStream_t s) {
     const int grid = grid_for(n, TILE);
-    auto launch = [&](auto kernel) -> int {
-        kernel<<<grid, TILE_THREADS, 0, s>>>(v, records, n, tol, pairs, window_cursor, out, weights);
+    auto launch = [&](auto binned, auto gathered) -> int {
+        if (in.records) binned<<<grid, TILE_THREADS, 0, s>>>(v, in, n, tol, pairs, window_cursor, out, weights);
+        else gathered<<<grid, TILE_THREADS, 0, s>>>(v, in, n, tol, pairs, window_cursor, out, weights);
         return CT_OK;
     };
     if (weights) {
-        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, 2>));
+        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, 2, false>, k_locate_points_binned<MAXV, true, 2, true>));
     } else if (MAXV <= 4)
-        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB>));
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB, false>, k_locate_points_binned<MAXV, false, CT_TILE_MINB, true>));
     else
-        CT_CHECK(launch(k_locate_points_binned<MAXV, false, 2>));
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, 2, false>, k_locate_points_binned<MAXV, false, 2, true>));
     CT_LAUNCH_CHECK();
     return CT_OK;
 }
 
 template <int MAXV>
 static int launch_locate_points(const TreeView &v, const double2 *pts, int64_t n, double tol, int64_t *out, double *weights,
-                                const uint32_t *perm, int32_t *in_order, cudaStream_t s) {
+                                const uint32_t *perm, int32_t *in_order, cudaStream_t s, uint2 *pairs = nullptr,
+                                uint32_t *window_cursor = nullptr) {
     int grid = grid_for(n, PER_THREAD * BLOCK);
     // 56 registers (9 blocks of 128 threads per SM) for the 3- and 4-vertex kernels: measured on C2, ms per 100 M points,
     // 64 regs 6.62, 56 regs 6.55, 48 regs 6.57, 40 regs 6.82 -- the cap hardly matters since the descent loop is lean
-    if (weights)
-        k_locate_points<MAXV, true, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
+    if (v.deep.slab) {  // a tree deeper than the per-thread stack
+        if (weights) k_locate_points<MAXV, true, 4, true><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order, pairs, window_cursor);
+        else k_locate_points<MAXV, false, 4, true><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order, pairs, window_cursor);
+    } else if (weights)
+        k_locate_points<MAXV, true, 8, false><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order, pairs, window_cursor);
     else if (MAXV <= 4)
-        k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
+        k_locate_points<(MAXV <= 4 ? MAXV : 4), false, 9, false><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order, pairs, window_cursor);
     else
-        k_locate_points<MAXV, false, 8><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order);
+        k_locate_points<MAXV, false, 8, false><<<grid, BLOCK, 0, s>>>(v, pts, n, tol, out, weights, perm, in_order, pairs, window_cursor);
     CT_LAUNCH_CHECK();
     return CT_OK;
 }
@@ -257,43 +331,99 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
                                 cudaStream_t s, bool profile = false) {
     if (n == 0) return CT_OK;
     TreeView v = tree->view();
+    DeepScope deep;
+    CT_CHECK(deep.init(tree, n, s));
+    CT_CHECK(deep.next_launch());
+    v.deep = deep.view;
     PhaseEvents *ev = profile ? phase_events() : nullptr;
     if (ev) CT_CUDA(cudaEventRecord(ev->start, s));
-    const bool binned = sort_bits_for(tree, n) > 0;
+    const bool binned = sort_bits_for(tree, n) > 0 && v.deep.slab == nullptr;  // deep trees: the simple kernel
     if (!binned) {
         // the caller's order: small batches, small trees
         if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
         int status = CT_OK;
         if (tree->kind == CT_KIND_EDGES) {
-            k_locate_points_on_edge<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, nullptr, nullptr);
+            if (v.deep.slab) k_locate_points_on_edge<true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, nullptr, nullptr);
+            else k_locate_points_on_edge<false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, pts, n, tol, out, nullptr, nullptr);
             CT_LAUNCH_CHECK();
         } else if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
         else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
         else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
         else status = launch_locate_points<32>(v, pts, n, tol, out, weights, nullptr, nullptr, s);
         if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
-        return status;
+        return status == CT_OK ? deep.finish() : status;
+    }
+    // Execution order (CELLTREE_ORDER, measured on C2 with 100 M points, step in ms): "bins" (default) moves the points into
+    // 16-bit Z-order bins (binning.cuh): 7.25; "sort" radix-sorts (bin, index) pairs and lets the tiles gather: 7.6 (the
+    // sort is 1.3 ms cheaper, the gathering traversal 1.7 ms dearer); "morton" is round 1's full 24-bit sort of (key, index)
+    // pairs with one gathered query per thread: 7.8 with the window queues.
+    static int order_mode = -1;
+    if (order_mode < 0) {
+        const char *e = getenv("CELLTREE_ORDER");
+        order_mode = (e && e[0] == 's') ? 1 : ((e && e[0] == 'm') ? 2 : 0);
+    }
+    if (order_mode == 2 && tree->kind == CT_KIND_FACES) {
+        // full Z-order sort of (key, index) pairs, one query per thread with the point gathered through the permutation
+        MortonOrder order;
+        CT_CHECK(order.build<KEY_POINT>(tree, reinterpret_cast<const double *>(pts), n, s));
+        const int64_t n_windows = (n + WINDOW - 1) >> WINDOW_BITS;
+        Scratch<uint2> pairs;
+        Scratch<uint32_t> window_cursor;
+        const bool queued = n > direct_out_limit();
+        if (queued) {
+            CT_CHECK(pairs.alloc(n, s));
+            CT_CHECK(window_cursor.alloc(n_windows, s));
+            CT_CUDA(cudaMemsetAsync(window_cursor.p, 0, n_windows * sizeof(uint32_t), s));
+        }
+        if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
+        int status;
+        if (tree->M == 3) status = launch_locate_points<3>(v, pts, n, tol, out, weights, order.perm, nullptr, s, pairs.p, window_cursor.p);
+        else if (tree->M == 4) status = launch_locate_points<4>(v, pts, n, tol, out, weights, order.perm, nullptr, s, pairs.p, window_cursor.p);
+        else if (tree->M <= 8) status = launch_locate_points<8>(v, pts, n, tol, out, weights, order.perm, nullptr, s, pairs.p, window_cursor.p);
+        else status = launch_locate_points<32>(v, pts, n, tol, out, weights, order.perm, nullptr, s, pairs.p, window_cursor.p);
+        if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
+        CT_CHECK(status);
+        if (queued) {
+            CT_CUDA(cudaFuncSetAttribute(k_windows_to_out, cudaFuncAttributeMaxDynamicSharedMemorySize, WINDOW * (int)sizeof(int32_t)));
+            k_windows_to_out<<<(unsigned)n_windows, WINDOW_THREADS, WINDOW * sizeof(int32_t), s>>>(pairs.p, n, out);
+            CT_LAUNCH_CHECK();
+        }
+        return deep.finish();
     }
     PointBins bins;
-    CT_CHECK(bins.build(tree, pts, n, s));
+    BinSort sorted;
+    TileInput in{nullptr, nullptr, pts, BinGrid{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy}};
+    if (order_mode == 0) {
+        CT_CHECK(bins.build(tree, pts, n, s));
+        in.records = bins.records.p;
+    } else {
+        CT_CHECK(sorted.build(in.grid, pts, n, s));
+        in.perm = sorted.perm;
+    }
+    Scratch<uint32_t> window_cursor;
+    const int64_t n_windows = (n + WINDOW - 1) >> WINDOW_BITS;
     Scratch<uint2> pairs;
     const bool queued = n > direct_out_limit();
-    if (queued) CT_CHECK(pairs.alloc(n, s));
+    if (queued) {
+        CT_CHECK(pairs.alloc(n, s));
+        CT_CHECK(window_cursor.alloc(n_windows, s));
+        CT_CUDA(cudaMemsetAsync(window_cursor.p, 0, n_windows * sizeof(uint32_t), s));
+    }
     if (ev) CT_CUDA(cudaEventRecord(ev->ordered, s));
     int status;
-    uint32_t *wc = bins.window_cursor();
-    if (tree->kind == CT_KIND_EDGES) status = launch_locate_points_binned<0>(v, bins.records.p, n, tol, pairs.p, wc, out, nullptr, s);
-    else if (tree->M == 3) status = launch_locate_points_binned<3>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
-    else if (tree->M == 4) status = launch_locate_points_binned<4>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
-    else if (tree->M <= 8) status = launch_locate_points_binned<8>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
-    else status = launch_locate_points_binned<32>(v, bins.records.p, n, tol, pairs.p, wc, out, weights, s);
+    uint32_t *wc = window_cursor.p;
+    if (tree->kind == CT_KIND_EDGES) status = launch_locate_points_binned<0>(v, in, n, tol, pairs.p, wc, out, nullptr, s);
+    else if (tree->M == 3) status = launch_locate_points_binned<3>(v, in, n, tol, pairs.p, wc, out, weights, s);
+    else if (tree->M == 4) status = launch_locate_points_binned<4>(v, in, n, tol, pairs.p, wc, out, weights, s);
+    else if (tree->M <= 8) status = launch_locate_points_binned<8>(v, in, n, tol, pairs.p, wc, out, weights, s);
+    else status = launch_locate_points_binned<32>(v, in, n, tol, pairs.p, wc, out, weights, s);
     if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
     if (status == CT_OK && queued) {
         CT_CUDA(cudaFuncSetAttribute(k_windows_to_out, cudaFuncAttributeMaxDynamicSharedMemorySize, WINDOW * (int)sizeof(int32_t)));
-        k_windows_to_out<<<(unsigned)bins.n_windows, WINDOW_THREADS, WINDOW * sizeof(int32_t), s>>>(pairs.p, n, out);
+        k_windows_to_out<<<(unsigned)n_windows, WINDOW_THREADS, WINDOW * sizeof(int32_t), s>>>(pairs.p, n, out);
         CT_LAUNCH_CHECK();
     }
-    return status;
+    return status == CT_OK ? deep.finish() : status;
 }
 
 }  // namespace ct
@@ -310,7 +440,6 @@ extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64
         set_error("ct_locate_points: barycentric weights need a face tree");
         return CT_ERR_VALUE;
     }
-    CT_CHECK(check_depth(tree));
     CT_ON_DEVICE(tree->device);
     cudaStream_t s = current_stream();
     if (mem == CT_MEM_DEVICE)
@@ -408,5 +537,109 @@ extern "C" int ct_profile_binning(const ct_tree *tree, const double *points, int
     *ms_per_run = ms / repeats;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return CT_OK;
+}
+
+// ---- diagnostics for the roofline line of bench.py -------------------------------------------------------------------
+namespace ct {
+template <int MAXV>
+__global__ void __launch_bounds__(BLOCK) k_locate_points_stats(TreeView t, const double2 *__restrict__ points, int64_t n, double tolerance,
+                                                               unsigned long long *__restrict__ stats) {
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    CountingProbe probe;
+    unsigned found = 0;
+    if (i < n) {
+        const double2 pt = points[i];
+        found = locate_point<MAXV, CountingProbe, true>(t, P2{pt.x, pt.y}, tolerance, &probe) >= 0 ? 1u : 0u;
+    }
+    const unsigned v[6] = {probe.slots, probe.headers, probe.cells, probe.pushes, probe.entries, found};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const unsigned sum = __reduce_add_sync(0xffffffffu, v[k]);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(stats + k, (unsigned long long)sum);
+    }
+}
+
+template <int BYTES>
+__global__ void __launch_bounds__(256) k_read_sweep(const uint4 *__restrict__ data, size_t n_words, int repeats, unsigned *__restrict__ sink) {
+    // every thread reads 16-byte words at a grid stride, `repeats` sweeps over the buffer
+    unsigned acc = 0;
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (int r = 0; r < repeats; r++)
+        for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < n_words; w += stride) {
+            uint4 q;
+            asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(data + w));
+            acc += q.x ^ q.y ^ q.z ^ q.w;
+        }
+    if (acc == 0x9e3779b9u) *sink = acc;  // keeps the loads alive
+}
+}  // namespace ct
+
+// What one launch of the point traversal touches, summed over the n queries (points on the device, caller's order):
+// stats[0] node slots read (16 B each), [1] treelet headers read (16 B), [2] cells tested (each: one row of elem_xy,
+// 16 B per vertex, and one row of elements), [3] siblings deferred to the stack, [4] queries that started from the
+// entry grid rather than the root, [5] queries that found a cell.
+extern "C" int ct_locate_points_stats(const ct_tree *tree, const double *points, int64_t n, double tolerance, int64_t *stats) {
+    if (!tree || !points || n <= 0 || !stats || tree->kind != CT_KIND_FACES) {
+        set_error("ct_locate_points_stats: bad argument (needs a face tree and device points)");
+        return CT_ERR_VALUE;
+    }
+    CT_ON_DEVICE(tree->device);
+    cudaStream_t s = current_stream();
+    TreeView v = tree->view();
+    DeepScope deep;
+    CT_CHECK(deep.init(tree, n, s));
+    CT_CHECK(deep.next_launch());
+    v.deep = deep.view;
+    Scratch<unsigned long long> d_stats;
+    CT_CHECK(d_stats.alloc(6, s));
+    CT_CUDA(cudaMemsetAsync(d_stats.p, 0, 6 * sizeof(unsigned long long), s));
+    const double2 *pts = reinterpret_cast<const double2 *>(points);
+    const int grid = grid_for(n, BLOCK);
+    if (tree->M == 3) k_locate_points_stats<3><<<grid, BLOCK, 0, s>>>(v, pts, n, tolerance, d_stats.p);
+    else if (tree->M == 4) k_locate_points_stats<4><<<grid, BLOCK, 0, s>>>(v, pts, n, tolerance, d_stats.p);
+    else if (tree->M <= 8) k_locate_points_stats<8><<<grid, BLOCK, 0, s>>>(v, pts, n, tolerance, d_stats.p);
+    else k_locate_points_stats<32><<<grid, BLOCK, 0, s>>>(v, pts, n, tolerance, d_stats.p);
+    CT_LAUNCH_CHECK();
+    unsigned long long h[6];
+    CT_CUDA(cudaMemcpyAsync(h, d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 6; k++) stats[k] = (int64_t)h[k];
+    return deep.finish();
+}
+
+// Read bandwidth of this GPU measured in place: `repeats` sweeps of 16-byte loads over a buffer of `bytes` bytes by a
+// grid that fills the machine.  A buffer well inside the L2 (64 MB of 126 MB) gives the L2 read rate after the first
+// sweep has brought it in; a buffer many times the L2 gives the HBM read rate.  The first sweep is not timed.
+extern "C" int ct_measure_read_bandwidth(size_t bytes, int32_t repeats, double *gb_per_s) {
+    if (bytes < 4096 || repeats < 1 || !gb_per_s) {
+        set_error("ct_measure_read_bandwidth: bad argument");
+        return CT_ERR_VALUE;
+    }
+    cudaStream_t s = current_stream();
+    Scratch<uint4> buffer;
+    Scratch<unsigned> sink;
+    const size_t words = bytes / 16;
+    CT_CHECK(buffer.alloc(words, s));
+    CT_CHECK(sink.alloc(1, s));
+    CT_CUDA(cudaMemsetAsync(buffer.p, 1, words * 16, s));
+    int device = 0, sms = 0;
+    CT_CUDA(cudaGetDevice(&device));
+    CT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = sms * 8;
+    cudaEvent_t e0, e1;
+    CT_CUDA(cudaEventCreate(&e0));
+    CT_CUDA(cudaEventCreate(&e1));
+    k_read_sweep<16><<<grid, 256, 0, s>>>(buffer.p, words, 1, sink.p);
+    CT_CUDA(cudaEventRecord(e0, s));
+    k_read_sweep<16><<<grid, 256, 0, s>>>(buffer.p, words, repeats, sink.p);
+    CT_CUDA(cudaEventRecord(e1, s));
+    CT_CUDA(cudaEventSynchronize(e1));
+    count_launch(2);
+    float ms = 0.f;
+    CT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gb_per_s = (double)words * 16.0 * repeats / (ms * 1e-3) / 1e9;
     return CT_OK;
 }

@@ -7,10 +7,9 @@
 // box / edge pairs -- is exactly the reference's.  The nodes are read through the treelets of common.cuh
 // (three levels per 128-byte line); a stack entry is a node handle (treelet << 3 | slot).
 //
-// The stack is a per-thread local array: it is thread-interleaved in local memory, so the 32 lanes of a
-// warp touch one 128-byte line per slot, and it stays in L1.  Live depth is at most (tree depth - 1):
-// one deferred sibling per level of the current path.  ct_tree.depth is checked against STACK_CAP before
-// any launch (CT_ERR_DEPTH instead of silent truncation).
+// The stack's first STACK_CAP entries are a per-thread local array: it is thread-interleaved in local memory, so the
+// 32 lanes of a warp touch one 128-byte line per slot, and it stays in L1.  Live depth is at most (tree depth - 1):
+// one deferred sibling per level of the current path; deeper trees continue in an overflow slab (Stack, below).
 //
 // Points walk in two nested loops (descend; then the leaf), their lanes move in step.  Boxes and segments walk
 // in one loop whose step has as few divergent paths as possible (the outcome of an inner node becomes selects and
@@ -21,7 +20,54 @@
 
 namespace ct {
 
+constexpr uint32_t ROOT_HANDLE_VALUE = 1u;
 constexpr int STACK_CAP = 64;
+
+// The reference's stack grows when it is full (utils.py:35-44, constants.py:136), so a tree of any depth is walked.
+// Here the first STACK_CAP entries are a per-thread array -- enough for every tree of at most STACK_CAP levels, i.e. for
+// every sane mesh -- and a thread whose stack outgrows them continues in a column of the tree's overflow slab
+// (common.cuh: DeepStacks; a cold, out-of-line path).
+// entry k of the overflow column of a thread (taken from the slab on first use); returns the column.  Out of line and by
+// value: the cold path must not force the caller's stack object into memory.
+static __device__ __noinline__ uint32_t *deep_stack_store(DeepStacks d, uint32_t *column, int k, uint32_t v) {
+    if (d.slab == nullptr) return column;  // unreachable for a tree whose depth the host has checked
+    if (column == nullptr) {
+        int c = atomicAdd(d.state, 1);
+        if (c >= d.slots) {  // no column left: the host reports CT_ERR_DEPTH, nothing of this launch is used
+            d.state[1] = 1;
+            c = 0;
+        }
+        column = d.slab + c;
+    }
+    column[(size_t)k * d.slots] = v;
+    return column;
+}
+
+// DEEP = false: the tree has at most STACK_CAP levels (the host checks), the stack is the plain per-thread array.
+// DEEP = true: kernels launched for deeper trees only; their stacks continue in the overflow slab.
+template <bool DEEP>
+struct StackT {
+    uint32_t local[STACK_CAP];
+    uint32_t *deep = nullptr;
+    int sp = 0;
+    CT_DEV bool empty() const { return sp == 0; }
+    CT_DEV void push(const TreeView &t, uint32_t v) {
+        if constexpr (DEEP) {
+            if (sp < STACK_CAP) local[sp] = v;
+            else deep = deep_stack_store(t.deep, deep, sp - STACK_CAP, v);
+            sp++;
+        } else {
+            local[sp++] = v;
+        }
+    }
+    CT_DEV uint32_t pop(const TreeView &t) {
+        --sp;
+        if constexpr (DEEP) {
+            if (sp >= STACK_CAP) return deep != nullptr ? deep[(size_t)(sp - STACK_CAP) * t.deep.slots] : ROOT_HANDLE_VALUE;
+        }
+        return local[sp];
+    }
+};
 
 // ---- the descent, shared by the four traversals ---------------------------------------------------------------
 // Cursor on one binary node = (treelet, slot), see common.cuh.  The node's 16-byte slot is loaded when the cursor
@@ -92,13 +138,47 @@ CT_DEV int leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices
 // Two nested loops: the inner one only descends (a handful of registers), the outer one tests the cells of the
 // leaf it arrived at (query.py:72-85) -- so that the register allocation of the descent is not weighed down by
 // the point-in-polygon test.
-template <int MAXV>
-CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
+// `Probe` counts what a walk touches (NoProbe: nothing, compiled away); ct_locate_points_stats uses it to state the bytes
+// the traversal as built has to move per query.
+struct NoProbe {
+    CT_DEV void slot() {}
+    CT_DEV void header() {}
+    CT_DEV void cell() {}
+    CT_DEV void push() {}
+    CT_DEV void entry(bool) {}
+};
+struct CountingProbe {
+    unsigned slots = 0, headers = 0, cells = 0, pushes = 0, entries = 0;
+    CT_DEV void slot() { slots++; }
+    CT_DEV void header() { headers++; }
+    CT_DEV void cell() { cells++; }
+    CT_DEV void push() { pushes++; }
+    CT_DEV void entry(bool from_grid) { entries += from_grid ? 1u : 0u; }
+};
+
+template <int MAXV, typename Probe = NoProbe, bool DEEP = false>
+CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe = nullptr) {
+    StackT<DEEP> stack;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
-    cursor_enter(c, base, entry_handle(t.entry, p));
+    Probe none;
+    Probe &pr = probe ? *probe : none;
+    // a move within a treelet reads the node's slot; entering a treelet reads its header as well
+    auto descend = [&](uint32_t child) {
+        pr.slot();
+        if ((c.handle & 7u) >= 4u) pr.header();
+        cursor_descend(c, base, child);
+    };
+    auto enter = [&](uint32_t handle) {
+        pr.slot();
+        pr.header();
+        cursor_enter(c, base, handle);
+    };
+    {
+        const uint32_t first = entry_handle(t.entry, p);
+        pr.entry(first != ROOT_HANDLE);
+        enter(first);
+    }
     while (true) {
         while (!cursor_is_leaf(c)) {
             const double Lmax = c.plane.x, Rmin = c.plane.y;
@@ -110,33 +190,35 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance) {
             if (left && right) {
                 // nearer-plane heuristic, query.py:93-101: the child pushed LAST is visited first
                 const bool right_first = (Lmax - pd) < (pd - Rmin);
-                stack[sp++] = right_first ? left_handle : right_handle;
-                cursor_descend(c, base, right_first ? right_handle : left_handle);
+                pr.push();
+                stack.push(t, right_first ? left_handle : right_handle);
+                descend(right_first ? right_handle : left_handle);
             } else if (left) {
-                cursor_descend(c, base, left_handle);
+                descend(left_handle);
             } else if (right) {
-                cursor_descend(c, base, right_handle);
+                descend(right_handle);
             } else {
-                if (sp == 0) return -1;
-                cursor_enter(c, base, stack[--sp]);
+                if (stack.empty()) return -1;
+                enter(stack.pop(t));
             }
         }
         const int4 leaf = cursor_leaf(c);
         for (int k = 0; k < leaf.y; k++) {
             int bbox_index = leaf_element(leaf, t.bb_indices, k);
             Poly<MAXV> poly;
-            load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, poly);
+            pr.cell();
+            load_tree_polygon<MAXV>(t, bbox_index, poly);
             if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
         }
-        if (sp == 0) return -1;
-        cursor_enter(c, base, stack[--sp]);
+        if (stack.empty()) return -1;
+        enter(stack.pop(t));
     }
 }
 
 // ---- locate_point_on_edge, query.py:121-165 ---------------------------------------------------------------
+template <bool DEEP = false>
 CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
+    StackT<DEEP> stack;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
     cursor_enter(c, base, entry_handle(t.entry, p));
@@ -150,15 +232,15 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
             cursor_children(c, left_handle, right_handle);
             if (left && right) {
                 const bool right_first = (Lmax - pd) < (pd - Rmin);
-                stack[sp++] = right_first ? left_handle : right_handle;
+                stack.push(t, right_first ? left_handle : right_handle);
                 cursor_descend(c, base, right_first ? right_handle : left_handle);
             } else if (left) {
                 cursor_descend(c, base, left_handle);
             } else if (right) {
                 cursor_descend(c, base, right_handle);
             } else {
-                if (sp == 0) return -1;
-                cursor_enter(c, base, stack[--sp]);
+                if (stack.empty()) return -1;
+                cursor_enter(c, base, stack.pop(t));
             }
         }
         const int4 leaf = cursor_leaf(c);
@@ -168,8 +250,8 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
             double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
             if (point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return bbox_index;
         }
-        if (sp == 0) return -1;
-        cursor_enter(c, base, stack[--sp]);
+        if (stack.empty()) return -1;
+        cursor_enter(c, base, stack.pop(t));
     }
 }
 
@@ -180,12 +262,11 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
 // lanes active per instruction), so the step is written with as few divergent paths as possible: one for a leaf,
 // one for an inner node whose outcome (left / right / both / neither) is turned into selects and a predicated push,
 // and a common tail that pops if needed and always loads header + slot of the next node.
-template <typename Emit>
+template <bool DEEP, typename Emit>
 CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
     Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
     if (!boxes_intersect(box, tree_bbox)) return 0;
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
+    StackT<DEEP> stack;
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
@@ -212,13 +293,13 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
             const bool right = bmax >= c.plane.y;
             uint32_t left_handle, right_handle;
             cursor_children(c, left_handle, right_handle);
-            if (left && right) stack[sp++] = left_handle;
+            if (left && right) stack.push(t, left_handle);
             next = right ? right_handle : left_handle;
             pop = !(left || right);
         }
         if (pop) {
-            if (sp == 0) return count;
-            next = stack[--sp];
+            if (stack.empty()) return count;
+            next = stack.pop(t);
         }
         cursor_enter(c, base, next);
     }
@@ -237,7 +318,7 @@ template <int MAXV>
 CT_DEV bool edge_face_clip(const TreeView &t, int bbox_index, P2 a, P2 b, P2 &c, P2 &d) {
     Box4 box = load_box(t.bb_coords, bbox_index);
     Poly<MAXV> polygon;
-    load_polygon<MAXV>(t.elements, t.M, bbox_index, t.elem_xy, polygon);
+    load_tree_polygon<MAXV>(t, bbox_index, polygon);
     double tolerance = nb_max(MIN_TOLERANCE, TOLERANCE_FACTOR * nb_max(box.xmax - box.xmin, box.ymax - box.ymin));
     return cyrus_beck_line_polygon_clip<MAXV>(a, b, polygon, tolerance, c, d);
 }
@@ -300,7 +381,7 @@ CT_DEV bool edge_cell_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
 
 // One thread walks one segment and tests every candidate as it meets it (the second traversal of the count -> fill
 // scheme; the first pass is the warp-cooperative kernel of edges.cu).
-template <int MAXV, typename Emit>
+template <int MAXV, bool DEEP, typename Emit>
 CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
     {
         P2 c, d;
@@ -308,8 +389,7 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
         if (!cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d)) return 0;
     }
     P2 V = to_vector(a, b);
-    uint32_t stack[STACK_CAP];
-    int sp = 0;
+    StackT<DEEP> stack;
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor cur;
@@ -333,13 +413,13 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
             edge_plane_test(cur, a, b, V, left, right);
             uint32_t left_handle, right_handle;
             cursor_children(cur, left_handle, right_handle);
-            if (left && right) stack[sp++] = left_handle;
+            if (left && right) stack.push(t, left_handle);
             next = right ? right_handle : left_handle;
             pop = !(left || right);
         }
         if (pop) {
-            if (sp == 0) return count;
-            next = stack[--sp];
+            if (stack.empty()) return count;
+            next = stack.pop(t);
         }
         cursor_enter(cur, base, next);
     }

@@ -27,19 +27,32 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, hi
 
 
+def _collective_device(device=None):
+    """Where the tensors of a collective must live: the given device, else the current CUDA device under NCCL, else the host."""
+    import torch
+    import torch.distributed as dist
+
+    if device is not None:
+        return torch.device(device)
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def exchange_totals(local_total: int, device=None):
     """
     One all-gather of the per-rank result sizes -> (global offset of this rank's first pair, grand total, all totals).
+    The path's only data-path collective: world_size int64 values.
     """
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size()
     rank = dist.get_rank()
-    mine = torch.tensor([int(local_total)], dtype=torch.int64, device=device)
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    totals = [int(t.item()) for t in gathered]
+    mine = torch.tensor([int(local_total)], dtype=torch.int64, device=_collective_device(device))
+    gathered = torch.empty(world, dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine)
+    totals = [int(t) for t in gathered.tolist()]
     return sum(totals[:rank]), sum(totals), totals
 
 
@@ -74,9 +87,9 @@ def query_pairs_sharded(tree, method: str, queries, *args, device=None):
     """
     This rank's share of a variable-length query -- `method` is one of ``locate_boxes``, ``intersect_boxes``,
     ``intersect_edges`` (queries = boxes / segments) -- over the contiguous range of `queries` this rank owns.
-    Returns ``(i_global, j, payload_or_None, offset, total)``: the local pairs with GLOBAL query indices, the position
-    of this rank's first pair in the concatenated (= single-GPU = reference) result and the grand total, obtained with
-    the path's one collective (an all-gather of the per-rank pair counts).
+    Returns ``(i_global, j, payload_or_None, offset, total, totals)``: the local pairs with GLOBAL query indices, the
+    position of this rank's first pair in the concatenated (= single-GPU = reference) result, the grand total and every
+    rank's count, obtained with the path's one collective (an all-gather of the per-rank pair counts).
     """
     import torch.distributed as dist
 
@@ -86,8 +99,8 @@ def query_pairs_sharded(tree, method: str, queries, *args, device=None):
     out = getattr(tree, method)(_rows(queries, lo, hi), *args)
     i_local, j = out[0], out[1]
     payload = out[2] if len(out) > 2 else None
-    offset, total, _ = exchange_totals(len(i_local), device=device)
-    return globalize_pairs(i_local, lo), j, payload, offset, total
+    offset, total, totals = exchange_totals(len(i_local), device=device)
+    return globalize_pairs(i_local, lo), j, payload, offset, total, totals
 
 
 def intersect_faces_sharded(tree, vertices, faces, fill_value: int, device=None):
@@ -100,39 +113,57 @@ def intersect_faces_sharded(tree, vertices, faces, fill_value: int, device=None)
 
     lo, hi = shard_range(len(faces), dist.get_rank(), dist.get_world_size())
     i_local, j, area = tree.intersect_faces(vertices, _rows(faces, lo, hi), fill_value)
-    offset, total, _ = exchange_totals(len(i_local), device=device)
-    return globalize_pairs(i_local, lo), j, area, offset, total
+    offset, total, totals = exchange_totals(len(i_local), device=device)
+    return globalize_pairs(i_local, lo), j, area, offset, total, totals
 
 
-def gather_pairs(i_global, j, payload, offset: int, total: int, dst: int = 0):
+def gather_pairs(i_global, j, payload, offset: int, total: int, totals=None, dst: int = 0):
     """
-    Assemble the sharded pairs on rank `dst` as host arrays in the reference's order (other ranks get None).
-    The ranks' pieces are variable-length, so this is an object gather of NumPy arrays: meant for results that must
-    end up on one host anyway; device-resident consumers keep their shard and use `offset`.
+    Assemble the sharded pairs on rank `dst` in the reference's order (other ranks get None).  Every rank's piece goes
+    straight to its place -- rows [offset, offset + count) of buffers preallocated on `dst` -- by point-to-point transfers:
+    CUDA tensors travel over NCCL (NVLink, device to device, nothing touches the host) and the result stays on `dst`'s
+    GPU; NumPy pieces travel as host tensors over whatever backend the group has and come back as NumPy arrays.
     """
+    import torch
     import torch.distributed as dist
 
-    def host(a):
-        if a is None or isinstance(a, np.ndarray):
-            return a
-        return a.detach().cpu().numpy()
-
-    piece = (int(offset), host(i_global), host(j), host(payload))
     rank, world = dist.get_rank(), dist.get_world_size()
-    pieces = [None] * world if rank == dst else None
-    dist.gather_object(piece, pieces, dst=dst)
+    if totals is None:
+        _, _, totals = exchange_totals(len(i_global))
+    on_device = not isinstance(i_global, np.ndarray)
+
+    def as_tensor(a):
+        if a is None:
+            return None
+        return torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a.contiguous()
+
+    pieces = [as_tensor(i_global), as_tensor(j), as_tensor(payload)]
+    if not on_device and dist.get_backend() == "nccl":
+        pieces = [None if p is None else p.to(_collective_device()) for p in pieces]
     if rank != dst:
+        for piece in pieces:
+            if piece is not None and piece.shape[0] > 0:
+                dist.send(piece, dst)
         return None
-    i_all = np.empty(total, dtype=np.intp)
-    j_all = np.empty(total, dtype=np.intp)
-    first_payload = next((p[3] for p in pieces if p[3] is not None), None)
-    p_all = None if first_payload is None else np.empty((total,) + first_payload.shape[1:], dtype=np.float64)
-    for off, pi, pj, pp in pieces:
-        i_all[off : off + len(pi)] = pi
-        j_all[off : off + len(pj)] = pj
-        if p_all is not None:
-            p_all[off : off + len(pi)] = pp
-    return i_all, j_all, p_all
+    starts = np.concatenate(([0], np.cumsum(totals)))
+    out = []
+    for piece in pieces:
+        if piece is None:
+            out.append(None)
+            continue
+        whole = torch.empty((int(total),) + tuple(piece.shape[1:]), dtype=piece.dtype, device=piece.device)
+        for r in range(world):
+            lo, hi = int(starts[r]), int(starts[r + 1])
+            if hi == lo:
+                continue
+            if r == dst:
+                whole[lo:hi] = piece
+            else:
+                dist.recv(whole[lo:hi], r)
+        out.append(whole)
+    if on_device:
+        return tuple(out)
+    return tuple(None if t is None else t.cpu().numpy() for t in out)
 
 
 def export_device_arrays(tree, device):

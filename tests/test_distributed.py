@@ -90,8 +90,9 @@ def _sharded_worker(rank, world, port, tmp):
         boxes = rng.uniform(0, 1, (777, 4))
         lo, hi, found = locate_points_sharded(tree, points)
         np.save(os.path.join(tmp, f"points{rank}.npy"), np.concatenate([[lo, hi], found]))
-        gi, j, area, offset, total = query_pairs_sharded(tree, "intersect_boxes", boxes)
-        gathered = gather_pairs(gi, j, area, offset, total, dst=0)
+        gi, j, area, offset, total, totals = query_pairs_sharded(tree, "intersect_boxes", boxes)
+        assert sum(totals) == total and sum(totals[:rank]) == offset
+        gathered = gather_pairs(gi, j, area, offset, total, totals, dst=0)
         if rank == 0:
             np.savez(os.path.join(tmp, "gathered.npz"), i=gathered[0], j=gathered[1], area=gathered[2])
         else:

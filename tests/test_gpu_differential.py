@@ -1,7 +1,7 @@
 """
 CUDA path vs the CPU oracle on seeded random inputs at sizes the oracle finishes in seconds, plus the edge
 cases the domain has: empty query sets, a single cell, everything outside, NaN coordinates, trees deeper than
-the traversal stack, device-resident inputs, and Morton ordering on/off.
+the per-thread traversal stack, device-resident inputs, and Morton ordering on/off.
 """
 
 import numpy as np
@@ -446,7 +446,21 @@ def geometric_strip(n):
     return vertices, faces
 
 
-def test_deep_tree_builds_bit_exact_and_traversal_depth_is_checked(pkg):
+def nested_strip(n):
+    """n quads [-x, 3x] x [0, 1] with x halving each time: all contain the origin and their centroids halve => a tree as
+    deep as the strip whose nodes all overlap, so a query near the origin defers a sibling at every level."""
+    x = 1.0 / 2.0 ** np.arange(n)
+    k = np.arange(n)
+    vertices = np.concatenate(
+        [np.column_stack((-x, np.zeros(n))), np.column_stack((3 * x, np.zeros(n))), np.column_stack((3 * x, np.ones(n))), np.column_stack((-x, np.ones(n)))]
+    )
+    faces = np.column_stack((k, k + n, k + 2 * n, k + 3 * n))
+    return vertices, faces
+
+
+def test_trees_deeper_than_the_per_thread_stack_are_walked(pkg):
+    """The reference's stack grows (utils.py:35-44): a tree of any depth is answered.  geometric_strip: deep but without
+    overlap (the stack stays shallow); nested_strip: 299 levels with every node overlapping (stacks of ~300 entries)."""
     vertices, faces = geometric_strip(60)
     tree = pkg.CellTree2d(vertices, faces, -1)
     ref = oracle.CellTree2d(vertices, faces, -1)
@@ -457,9 +471,38 @@ def test_deep_tree_builds_bit_exact_and_traversal_depth_is_checked(pkg):
     tree = pkg.CellTree2d(vertices, faces, -1)
     ref = oracle.CellTree2d(vertices, faces, -1)
     assert_same_tree(tree, ref)
-    if tree.depth > 64:
-        with pytest.raises(RuntimeError, match="levels"):
-            tree.locate_points(pts)
+    assert tree.depth > 64
+    assert np.array_equal(tree.locate_points(pts), ref.locate_points(pts))
+
+    n = 300
+    vertices, faces = nested_strip(n)
+    tree = pkg.CellTree2d(vertices, faces, -1)
+    ref = oracle.CellTree2d(vertices, faces, -1)
+    assert_same_tree(tree, ref)
+    assert tree.depth > 250
+    rng = np.random.default_rng(1)
+    m = 20_000
+    pts = np.column_stack((rng.choice([-1.0, 1.0], m) * 2.0 ** -rng.uniform(0, n + 5, m), rng.uniform(-0.1, 1.1, m)))
+    i, w = tree.compute_barycentric_weights(pts)
+    ri, rw = ref.compute_barycentric_weights(pts)
+    assert np.array_equal(i, ri) and np.array_equal(w, rw)
+    assert len(np.unique(i)) > 200
+    boxes = np.column_stack((-(2.0 ** -rng.uniform(0, n, 2000)), 2.0 ** -rng.uniform(0, n, 2000), rng.uniform(0, 0.4, 2000), rng.uniform(0.5, 1, 2000)))
+    bi, bj = tree.locate_boxes(boxes)
+    rbi, rbj = ref.locate_boxes(boxes)
+    assert np.array_equal(bi, rbi) and np.array_equal(bj, rbj) and len(bi) > 100_000
+    ai, aj, area = tree.intersect_boxes(boxes)
+    rai, raj, rarea = ref.intersect_boxes(boxes)
+    assert np.array_equal(ai, rai) and np.array_equal(aj, raj) and np.array_equal(area, rarea)
+    a = np.column_stack((-(2.0 ** -rng.uniform(0, n, 1500)), rng.uniform(0, 1, 1500)))
+    b = np.column_stack((2.0 ** -rng.uniform(0, n, 1500), rng.uniform(0, 1, 1500)))
+    segments = np.stack((a, b), axis=1)
+    ei, ej, xy = tree.intersect_edges(segments)
+    rei, rej, rxy = ref.intersect_edges(segments)
+    assert np.array_equal(ei, rei) and np.array_equal(ej, rej) and np.array_equal(xy, rxy, equal_nan=True)
+    # device-resident, Morton / binned order (a batch large enough to be ordered)
+    big = np.column_stack((rng.choice([-1.0, 1.0], 400_000) * 2.0 ** -rng.uniform(0, n + 5, 400_000), rng.uniform(0, 1, 400_000)))
+    assert np.array_equal(tree.locate_points(big), ref.locate_points(big))
 
 
 def test_unbucketable_centroid_raises_like_the_reference(pkg):
