@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     }
     const P2 V = to_vector(a, b);
     const char *base = reinterpret_cast<const char *>(t.treelets);
-    StackT<false> stack;  // deep trees take the per-thread count / fill kernels instead (run_edges)
+    CT_STACK(stack, false);  // deep trees take the per-thread count / fill kernels instead (run_edges)
     Cursor cur;
     cursor_enter(cur, base, ROOT_HANDLE);
     int leaf_k = 0;    // cells of the current leaf already pushed

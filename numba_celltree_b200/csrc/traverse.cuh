@@ -45,11 +45,15 @@ static __device__ __noinline__ uint32_t *deep_stack_store(DeepStacks d, uint32_t
 
 // DEEP = false: the tree has at most STACK_CAP levels (the host checks), the stack is the plain per-thread array.
 // DEEP = true: kernels launched for deeper trees only; their stacks continue in the overflow slab.
+// The per-thread array is declared by the caller (CT_STACK) and only pointed to from here: with the array inside this
+// struct the compiler keeps the WHOLE struct in local memory (the array is indexed dynamically), stack pointer included,
+// and every push / pop / empty test becomes a local load (measured: +6 % on the box and segment walks).
 template <bool DEEP>
 struct StackT {
-    uint32_t local[STACK_CAP];
+    uint32_t *local;
     uint32_t *deep = nullptr;
     int sp = 0;
+    CT_DEV explicit StackT(uint32_t *memory) : local(memory) {}
     CT_DEV bool empty() const { return sp == 0; }
     CT_DEV void push(const TreeView &t, uint32_t v) {
         if constexpr (DEEP) {
@@ -68,6 +72,10 @@ struct StackT {
         return local[sp];
     }
 };
+
+#define CT_STACK(name, DEEP_FLAG)          \
+    uint32_t name##_memory[STACK_CAP];     \
+    StackT<DEEP_FLAG> name(name##_memory)
 
 // ---- the descent, shared by the four traversals ---------------------------------------------------------------
 // Cursor on one binary node = (treelet, slot), see common.cuh.  The node's 16-byte slot is loaded when the cursor
@@ -158,7 +166,7 @@ struct CountingProbe {
 
 template <int MAXV, typename Probe = NoProbe, bool DEEP = false>
 CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe = nullptr) {
-    StackT<DEEP> stack;
+    CT_STACK(stack, DEEP);
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
     Probe none;
@@ -218,7 +226,7 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe 
 // ---- locate_point_on_edge, query.py:121-165 ---------------------------------------------------------------
 template <bool DEEP = false>
 CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
-    StackT<DEEP> stack;
+    CT_STACK(stack, DEEP);
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
     cursor_enter(c, base, entry_handle(t.entry, p));
@@ -266,7 +274,7 @@ template <bool DEEP, typename Emit>
 CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
     Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
     if (!boxes_intersect(box, tree_bbox)) return 0;
-    StackT<DEEP> stack;
+    CT_STACK(stack, DEEP);
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor c;
@@ -389,7 +397,7 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
         if (!cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d)) return 0;
     }
     P2 V = to_vector(a, b);
-    StackT<DEEP> stack;
+    CT_STACK(stack, DEEP);
     int count = 0;
     const char *base = reinterpret_cast<const char *>(t.treelets);
     Cursor cur;
