@@ -11,17 +11,23 @@ One "step" = one locate_points pass over the whole batch.
   value      device-resident throughput: points and results live in HBM, CUDA events around K steps.
   e2e        the same call through the public API with HOST (pinned) buffers: host->device copy of the
              points and device->host copy of the indices inside the timed region.
-  roofline   dominant kernel (k_locate_points): algorithmic bytes (918 B/query at C2) x queries
-             / its launch duration (CUDA events on the launching stream), against the measured HBM copy peak;
-             `traffic` is that kernel's DRAM bytes per launch from the ncu capture named in profiles/traffic.json.
-  cpu_baseline  the CPU oracle (C restatement of the reference's algorithm, OpenMP over queries like the
-             reference's prange) timed on this box's host cores on a bounded prefix of the same points.
+  roofline   dominant kernel (the traversal, k_locate_points_binned): the bytes that kernel as built reads and writes per
+             query -- counted by an instrumented run of the same walk (ct_locate_points_stats) -- x queries / its launch
+             duration (CUDA events on the launching stream), against the measured HBM peak; the L2 and HBM read rates are
+             measured in the run as well; `traffic` is the kernel's DRAM bytes per launch from the ncu capture named in
+             profiles/traffic.json, used only if that capture was taken from the kernel sources that are running.
+  cpu_baseline  the reference itself (numba_celltree under Numba, vendored to baseline/_ref by baseline/vendor_ref.py): its
+             query.locate_points on a bounded prefix of the same points, all host cores; the C port of oracle/ beside it.
+  secondary  driver-run lines for the other BASELINE.json configurations (C2 weights, C3 boxes, C4 segments, C5 faces, C1 on
+             the CPU reference).
 
-Multi-GPU (torchrun, one rank per GPU): the tree is built on rank 0 and replicated by NCCL broadcast over
-NVLink; queries shard by rank with no data-path collective (weak scaling: every rank owns a full batch).
+Multi-GPU (torchrun, one rank per GPU): the tree is built on rank 0 and replicated by NCCL broadcast over NVLink.  `value`
+is weak scaling (every rank owns a full batch, no data-path collective); `strong_scaling` splits the ONE batch by
+shard_range and assembles the results on every GPU; `multi_gpu` times the sharded variable-length calls with their one
+all-gather; `parity_multi` compares rank 0 alone with the assembled shards.
 
---impl reference times the CPU oracle alone (all host threads) on the same configuration, each step a
-bounded prefix of the batch.
+--impl reference times the UNMODIFIED reference (Numba prange, all host cores) on the same configuration; the C/OpenMP
+port only if the reference cannot be imported, and then says so.
 """
 
 from __future__ import annotations
@@ -779,6 +785,24 @@ def main():
         "ms_per_step": 1e3 * e2e_s / args.steps,
     }
     same = bool(torch.equal(dev_out.cpu(), host_out))
+    # the floor of that figure: the two copies alone (pinned host <-> device, both directions at once, every rank at the
+    # same time) -- what the host side of this box can move, whatever the kernels do
+    copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def bare_copies():
+        with torch.cuda.stream(copy_in):
+            dev_points.copy_(host_points, non_blocking=True)
+        with torch.cuda.stream(copy_out):
+            host_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    bare_copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        bare_copies()
+    e2e["host_copy_floor_ms"] = 1e3 * max_over_ranks(time.perf_counter() - t0) / 3
+    e2e["overhead_over_copies"] = e2e["ms_per_step"] / e2e["host_copy_floor_ms"] - 1.0
 
     # ---- CPU baseline + parity (rank 0, single-GPU run only) ------------------------------------------------
     cpu_baseline = None

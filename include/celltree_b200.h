@@ -35,8 +35,10 @@ extern "C" {
 #define CT_ERR_CUDA 1          /* CUDA runtime error (no device, out of memory, launch failure) */
 #define CT_ERR_VALUE 2         /* invalid argument (maps to Python ValueError) */
 #define CT_ERR_UNBUCKETABLE 3  /* tree build: an element's centroid falls in no bucket (reference: IndexError, creation.py:130-131) */
-#define CT_ERR_DEPTH 4         /* tree deeper than the compiled traversal stack capacity */
+#define CT_ERR_DEPTH 4         /* more queries of one call overflowed the per-thread traversal stack than the overflow slab holds */
 #define CT_ERR_CLIP_STATE 5    /* "Undefined clipping state" (cohen_sutherland.py:86) */
+#define CT_ERR_ZERO_DIVISION 6 /* barycentric weights: a division by exactly zero, where the reference (Numba, Python error
+                                  model) raises ZeroDivisionError: barycentric_wachspress.py:34,76,83, barycentric_triangle.py:36 */
 
 #define CT_MEM_HOST 0
 #define CT_MEM_DEVICE 1

@@ -21,6 +21,7 @@ CT_ERR_VALUE = 2
 CT_ERR_UNBUCKETABLE = 3
 CT_ERR_DEPTH = 4
 CT_ERR_CLIP_STATE = 5
+CT_ERR_ZERO_DIVISION = 6
 CT_MEM_HOST = 0
 CT_MEM_DEVICE = 1
 CT_KIND_FACES = 0
@@ -127,6 +128,8 @@ def check(status: int) -> None:
         raise ValueError(message)
     if status == CT_ERR_UNBUCKETABLE:
         raise IndexError(message)
+    if status == CT_ERR_ZERO_DIVISION:
+        raise ZeroDivisionError(message)
     raise RuntimeError(f"libcelltree_b200 error {status}: {message}")
 
 

@@ -32,6 +32,8 @@ class CellTree2d(CellTree2dBase):
     cells_per_leaf: int, optional, default: 2 (>= 1)
     """
 
+    _KIND = _lib.CT_KIND_FACES
+
     def __init__(
         self,
         vertices: FloatArray,

@@ -96,6 +96,7 @@ class DeviceTree:
 
 class CellTree2dBase(abc.ABC):
     _tree: DeviceTree
+    _KIND: int  # _lib.CT_KIND_FACES or _lib.CT_KIND_EDGES, set by the two concrete classes
 
     # ---- mirrors of the device arrays (downloaded on first access, then cached and writable) -------------
     def _download(self, name: str):
@@ -266,7 +267,7 @@ class CellTree2dBase(abc.ABC):
         """Read a tree written by :meth:`save`: the arrays are uploaded as they are, no build kernels run."""
         with np.load(file) as z:
             kind = int(z["kind"])
-            expected = _lib.CT_KIND_FACES if cls.__name__ == "CellTree2d" else _lib.CT_KIND_EDGES
+            expected = cls._KIND  # a class attribute: subclasses of either tree load like their parent
             if kind != expected:
                 raise ValueError(f"{file} holds a {'face' if kind == _lib.CT_KIND_FACES else 'edge'} tree")
             return cls._from_arrays(

@@ -59,9 +59,8 @@ __global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const d
     s_hits[warp][lane] = 0;
     bool active = false;
     if (valid) {
-        P2 c, d;
         Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
-        active = cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d) != 0;
+        active = cohen_sutherland_line_meets_box(a, b, tree_bbox);
     }
     const P2 V = to_vector(a, b);
     const char *base = reinterpret_cast<const char *>(t.treelets);

@@ -287,10 +287,16 @@ CT_DEV int get_clip(P2 a, const Box4 &box) {  // cohen_sutherland.py:18-33
 // cohen_sutherland.py:36-101.  Returns 1 (c, d = clipped segment), 0 (no intersection; c, d = NaN).
 // The reference's "Undefined clipping state" branch is unreachable (a non-zero outcode has one of the
 // four bits set), so there is no error return.
-static __device__ __noinline__ int cohen_sutherland_line_box_clip(P2 a, P2 b, Box4 box, P2 &c, P2 &d) {
+// WANT_POINTS = false: only whether the segment meets the box (the prefilter of the segment queries, query.py:316-319,
+// throws the clipped points away).  The function is out of line, so its outputs go through memory: without them the
+// segment walk saves eight 8-byte local stores per candidate (1.4 G of its 1.8 G local store sectors on C4).
+template <bool WANT_POINTS>
+static __device__ __noinline__ int cohen_sutherland_clip(P2 a, P2 b, Box4 box, P2 *c, P2 *d) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    c = P2{nan, nan};
-    d = P2{nan, nan};
+    if constexpr (WANT_POINTS) {
+        *c = P2{nan, nan};
+        *d = P2{nan, nan};
+    }
     double dx = b.x - a.x;
     double dy = b.y - a.y;
     if (dx == 0.0 && dy == 0.0) return 0;
@@ -313,10 +319,14 @@ static __device__ __noinline__ int cohen_sutherland_line_box_clip(P2 a, P2 b, Bo
         dy = b.y - a.y;
         if (dx == 0.0 && dy == 0.0) return 0;
     }
-    c = a;
-    d = b;
+    if constexpr (WANT_POINTS) {
+        *c = a;
+        *d = b;
+    }
     return 1;
 }
+CT_DEV int cohen_sutherland_line_box_clip(P2 a, P2 b, Box4 box, P2 &c, P2 &d) { return cohen_sutherland_clip<true>(a, b, box, &c, &d); }
+CT_DEV bool cohen_sutherland_line_meets_box(P2 a, P2 b, Box4 box) { return cohen_sutherland_clip<false>(a, b, box, nullptr, nullptr) != 0; }
 
 // ---- Cyrus-Beck / Skala segment / convex polygon: algorithms/cyrus_beck.py -----------------------------
 CT_DEV bool cb_compute_intersection(P2 a, P2 s, P2 v0, P2 v1, double &t) {  // cyrus_beck.py:35-52
@@ -477,15 +487,17 @@ CT_DEV double polygon_area(Work &work, int buffer, int length) {
 
 // polygon_polygon_clip_area, sutherland_hodgman.py:84-148: clip `polygon` (subject) by every edge of
 // `clipper`; zero-length clipper / subject edges are skipped; early 0.0 when fewer than 3 vertices remain.
-// The working polygons hold at most MAXA + MAXB vertices (a convex subject gains at most one vertex per
-// clip edge); the reference sizes them 2 * MAX_N_VERTEX = 64 and copies the output back into the subject
-// after every clip edge, here the two buffers swap roles.
-template <int MAXA, int MAXB, typename Work>
-CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MAXB> &clipper, Work &work) {
-    constexpr int CAP = MAXA + MAXB;
+// The reference sizes its working polygons 2 * MAX_N_VERTEX = 64 and copies the output back into the subject after
+// every clip edge; here two buffers of CAP vertices swap roles.  A convex subject gains at most one vertex per clip
+// edge, so CAP = MAXA + MAXB holds it; a concave or self-intersecting cell can gain more (up to one per subject edge
+// and clip edge): `overflow` is then set instead of dropping a vertex, and the caller repeats the pair with the
+// reference's capacity.
+template <int MAXA, int MAXB, int CAP, typename Work>
+CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MAXB> &clipper, Work &work, bool &overflow) {
     int n_output = polygon.n;
     const int n_clip = clipper.n;
     int out = 0;  // buffer that holds the current output polygon
+    overflow = false;
 #pragma unroll
     for (int i = 0; i < MAXA; i++)
         if (i < n_output) work.at(out, i) = make_double2(polygon.x[i], polygon.y[i]);
@@ -506,6 +518,8 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
             if (n_output < CAP) {
                 work.at(out, n_output) = make_double2(v.x, v.y);
                 n_output++;
+            } else {
+                overflow = true;
             }
         };
         const double2 last = work.at(in, length - 1);
@@ -535,10 +549,19 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
             a = b;
             a_inside = b_inside;
         }
+        if (overflow) return 0.0;
         if (n_output < 3) return 0.0;
         r = s;
     }
     return polygon_area(work, out, n_output);
+}
+
+// the pair again with working polygons of the reference's size (out of line: almost never taken)
+template <int MAXA, int MAXB>
+__device__ __noinline__ double clip_area_full_capacity(const Poly<MAXA> &a, const Poly<MAXB> &b) {
+    LocalClipWork<2 * MAX_N_VERTEX> work;
+    bool overflow;
+    return polygon_polygon_clip_area<MAXA, MAXB, 2 * MAX_N_VERTEX>(a, b, work, overflow);
 }
 
 // The per-pair kernels' entry: shared-memory working polygons for the small bounds, per-thread arrays otherwise.
@@ -546,14 +569,18 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
 template <int MAXA, int MAXB, int THREADS>
 CT_DEV double clip_area_of_pair(const Poly<MAXA> &a, const Poly<MAXB> &b) {
     constexpr int CAP = MAXA + MAXB;
+    bool overflow;
+    double area;
     if constexpr (CAP <= 8) {
         __shared__ double2 storage[2 * CAP * THREADS];
         SharedClipWork<CAP> work{storage + threadIdx.x, THREADS};
-        return polygon_polygon_clip_area<MAXA, MAXB>(a, b, work);
+        area = polygon_polygon_clip_area<MAXA, MAXB, CAP>(a, b, work, overflow);
     } else {
         LocalClipWork<CAP> work;
-        return polygon_polygon_clip_area<MAXA, MAXB>(a, b, work);
+        area = polygon_polygon_clip_area<MAXA, MAXB, CAP>(a, b, work, overflow);
     }
+    if (overflow) area = clip_area_full_capacity<MAXA, MAXB>(a, b);
+    return area;
 }
 
 // ---- separating axis test: algorithms/separating_axis.py -----------------------------------------------
@@ -592,6 +619,8 @@ CT_DEV bool separating_axes(const Poly<MAXA> &a, const Poly<MAXB> &b) {
 
 // ---- barycentric weights ---------------------------------------------------------------------------------
 // algorithms/barycentric_triangle.py:28-43
+// A triangle of zero area gives 1.0 / 0.0 = inf and NaN weights, in the reference as here: its compute_weights is inlined
+// into the parallel loop, where Numba's division does not raise (measured: NaN rows, no exception, any batch size).
 CT_DEV void triangle_weights(P2 a, P2 b, P2 c, P2 p, double &u, double &v, double &w) {
     P2 ab = to_vector(a, b);
     P2 ac = to_vector(a, c);
@@ -607,8 +636,14 @@ CT_DEV void triangle_weights(P2 a, P2 b, P2 c, P2 p, double &u, double &v, doubl
 
 // algorithms/barycentric_wachspress.py:38-85 (+ interp_edge_case :26-35).  w[] has MAXV slots, all
 // pre-zeroed by the caller; slots >= poly.n stay zero (the reference's rows are n_max_vert wide).
+// `zero_division` is set where this function divides by exactly zero.  The reference's compute_weights is a separate
+// @njit function with Python's error model, so it raises ZeroDivisionError there -- inside a prange loop, where what
+// happens next is undefined: measured with Numba 0.65 / OpenMP layer on a point exactly on an edge with tolerance=0.0,
+// the call raises for a batch of one, and for larger batches returns normally with the rows of the rest of the failing
+// thread's chunk left zero (125 of 1000, 12 500 of 100 000).  The library takes the defined behaviour: the host turns
+// the flag into ZeroDivisionError, always.
 template <int MAXV>
-CT_DEV void wachspress_weights(const Poly<MAXV> &polygon, P2 p, double tolerance, double (&w)[MAXV]) {
+CT_DEV void wachspress_weights(const Poly<MAXV> &polygon, P2 p, double tolerance, double (&w)[MAXV], int *zero_division = nullptr) {
     const int n = polygon.n;
     double w_sum = 0.0;
     P2 a = pget(polygon, n - 1);
@@ -622,7 +657,9 @@ CT_DEV void wachspress_weights(const Poly<MAXV> &polygon, P2 p, double tolerance
         ei = n - 1;
         ej = 0;
         P2 V2 = to_vector(a, p);
-        ew = sqrt(dot_product(V2, V2)) / sqrt(dot_product(U, U));
+        const double length = sqrt(dot_product(U, U));
+        if (length == 0.0 && zero_division) *zero_division = 1;
+        ew = sqrt(dot_product(V2, V2)) / length;
     } else {
 #pragma unroll
         for (int i = 0; i < MAXV; i++) {
@@ -638,9 +675,12 @@ CT_DEV void wachspress_weights(const Poly<MAXV> &polygon, P2 p, double tolerance
                 ei = i;
                 ej = i_next;
                 P2 V2 = to_vector(b, p);
-                ew = sqrt(dot_product(V2, V2)) / sqrt(dot_product(U, U));
+                const double length = sqrt(dot_product(U, U));
+                if (length == 0.0 && zero_division) *zero_division = 1;
+                ew = sqrt(dot_product(V2, V2)) / length;
                 break;
             }
+            if ((Ai * Aj) == 0.0 && zero_division) *zero_division = 1;
             double wi = 2 * Ci / (Ai * Aj);
             w[i] = wi;
             w_sum += wi;
@@ -659,6 +699,7 @@ CT_DEV void wachspress_weights(const Poly<MAXV> &polygon, P2 p, double tolerance
         }
         return;
     }
+    if (w_sum == 0.0 && zero_division) *zero_division = 1;
 #pragma unroll
     for (int i = 0; i < MAXV; i++)
         if (i < n) w[i] /= w_sum;

@@ -21,6 +21,9 @@ CT_DEV void async_copy_16(void *smem_dst, const void *gmem_src) {
 }
 CT_DEV void async_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// set by the weight kernels where the reference would raise ZeroDivisionError (geometry.cuh); read and cleared by the host
+__device__ int g_zero_division;
+
 template <int MAXV, bool WEIGHTS>
 CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, double *__restrict__ w_out) {
     const int M = t.M;
@@ -39,7 +42,7 @@ CT_DEV void write_weights(const TreeView &t, int found, P2 p, double tolerance, 
         double w[MAXV];
 #pragma unroll
         for (int k = 0; k < MAXV; k++) w[k] = 0.0;
-        if (found != -1) wachspress_weights<MAXV>(poly, p, tolerance, w);
+        if (found != -1) wachspress_weights<MAXV>(poly, p, tolerance, w, &g_zero_division);
         if constexpr (MAXV == 4) {
             if (M == 4) {
                 double2 *o = reinterpret_cast<double2 *>(w_out);
@@ -430,8 +433,32 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
 
 using namespace ct;
 
+// after a call that computed weights: did a kernel divide by zero where the reference raises?
+static int check_zero_division(cudaStream_t s) {
+    int flag = 0;
+    CT_CUDA(cudaMemcpyFromSymbolAsync(&flag, g_zero_division, sizeof(int), 0, cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    if (!flag) return CT_OK;
+    const int zero = 0;
+    CT_CUDA(cudaMemcpyToSymbolAsync(g_zero_division, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, s));
+    CT_CUDA(cudaStreamSynchronize(s));
+    set_error("division by zero");
+    return CT_ERR_ZERO_DIVISION;
+}
+
+static int locate_points_entry(const ct_tree *tree, const double *points, int64_t n, double tolerance, int64_t *out_index, double *weights,
+                               int32_t mem);
+
 extern "C" int ct_locate_points(const ct_tree *tree, const double *points, int64_t n, double tolerance, int64_t *out_index,
                                 double *weights, int32_t mem) {
+    const int status = locate_points_entry(tree, points, n, tolerance, out_index, weights, mem);
+    if (status != CT_OK || !weights || n == 0) return status;
+    CT_ON_DEVICE(tree->device);
+    return check_zero_division(current_stream());
+}
+
+static int locate_points_entry(const ct_tree *tree, const double *points, int64_t n, double tolerance, int64_t *out_index, double *weights,
+                               int32_t mem) {
     if (!tree || n < 0 || (n > 0 && (!points || !out_index))) {
         set_error("ct_locate_points: null argument");
         return CT_ERR_VALUE;

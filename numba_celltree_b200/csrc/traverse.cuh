@@ -318,8 +318,7 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
 // bounding box decides whether the cell is looked at at all (its clipped points are not used further) ...
 CT_DEV bool edge_face_prefilter(const TreeView &t, int bbox_index, P2 a, P2 b) {
     Box4 box = load_box(t.bb_coords, bbox_index);
-    P2 c, d;
-    return cohen_sutherland_line_box_clip(a, b, box, c, d) != 0;
+    return cohen_sutherland_line_meets_box(a, b, box);
 }
 // ... and the Cyrus-Beck clip against the cell's polygon gives the intersection
 template <int MAXV>
@@ -392,9 +391,8 @@ CT_DEV bool edge_cell_intersect(const TreeView &t, int bbox_index, P2 a, P2 b, P
 template <int MAXV, bool DEEP, typename Emit>
 CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
     {
-        P2 c, d;
         Box4 tree_bbox{t.bbox[0], t.bbox[1], t.bbox[2], t.bbox[3]};
-        if (!cohen_sutherland_line_box_clip(a, b, tree_bbox, c, d)) return 0;
+        if (!cohen_sutherland_line_meets_box(a, b, tree_bbox)) return 0;
     }
     P2 V = to_vector(a, b);
     CT_STACK(stack, DEEP);

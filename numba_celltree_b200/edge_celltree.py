@@ -27,6 +27,8 @@ class EdgeCellTree2d(CellTree2dBase):
     cells_per_leaf: int, optional, default: 2 (>= 1)
     """
 
+    _KIND = _lib.CT_KIND_EDGES
+
     def __init__(self, vertices: FloatArray, edges: IntArray, n_buckets: int = 4, cells_per_leaf: int = 2):
         if n_buckets < 2:
             raise ValueError("n_buckets must be >= 2")

@@ -106,3 +106,57 @@ def test_tensors_of_another_gpu_are_refused_and_the_current_device_is_kept():
         assert torch.cuda.current_device() == 1
     finally:
         torch.cuda.set_device(0)
+
+
+def test_concave_cells_overflowing_the_small_clip_buffers():
+    """The clip's working polygons hold MAXA + MAXB vertices, enough for convex cells; a concave or self-intersecting cell
+    can make the clipped polygon grow beyond that, and the pair is then repeated with the reference's capacity (64)."""
+    import numba_celltree_b200 as pkg
+
+    rng = np.random.default_rng(8)
+    n = 30
+    xs, ys = np.meshgrid(np.arange(n, dtype=float), np.arange(n, dtype=float), indexing="xy")
+    base = np.column_stack((xs.ravel(), ys.ravel()))
+    # darts (concave quads) and bow ties (self-intersecting quads), counter-clockwise where that means anything
+    dart = np.array([[0.0, 0.0], [0.9, 0.45], [0.0, 0.9], [0.35, 0.45]])
+    bow = np.array([[0.0, 0.0], [0.9, 0.9], [0.9, 0.0], [0.0, 0.9]])
+    shapes = np.where((rng.random(len(base)) < 0.5)[:, None, None], dart, bow)
+    vertices = (base[:, None, :] + shapes).reshape(-1, 2)
+    faces = np.arange(len(vertices)).reshape(-1, 4)
+    tree, ref = pkg.CellTree2d(vertices, faces, -1), oracle.CellTree2d(vertices, faces, -1)
+    c = rng.uniform(0, n, (20_000, 2))
+    wh = rng.uniform(0.05, 2.5, (20_000, 2))
+    boxes = np.column_stack((c[:, 0] - wh[:, 0] / 2, c[:, 0] + wh[:, 0] / 2, c[:, 1] - wh[:, 1] / 2, c[:, 1] + wh[:, 1] / 2))
+    i, j, a = tree.intersect_boxes(boxes)
+    ri, rj, ra = ref.intersect_boxes(boxes)
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra) and len(i) > 10_000
+    # the same cells as a query mesh over themselves, shifted: concave subject AND concave clipper
+    shifted = vertices + [0.3, 0.2]
+    fi, fj, fa = tree.intersect_faces(shifted, faces, -1)
+    rfi, rfj, rfa = ref.intersect_faces(shifted, faces, -1)
+    assert np.array_equal(fi, rfi) and np.array_equal(fj, rfj) and np.array_equal(fa, rfa) and len(fi) > 300
+
+
+def test_division_by_zero_in_the_weights():
+    """Wachspress weights with tolerance=0.0 for a point exactly on an edge divide by zero.  The reference raises
+    ZeroDivisionError inside its prange loop, with undefined consequences (measured: the exception for a batch of one, a
+    normal return with part of the rows left zero for larger batches); the library always raises.  A triangle of zero area
+    gives NaN weights in both."""
+    import numba_celltree_b200 as pkg
+    from numba_celltree_b200.synthetic import quad_mesh
+
+    v, f = quad_mesh(4, 4)
+    tree = pkg.CellTree2d(v, f, -1)
+    pts = np.random.default_rng(0).uniform(0, 1, (1000, 2))
+    i, w = tree.compute_barycentric_weights(pts, tolerance=0.0)  # no point on an edge: fine
+    assert np.allclose(w.sum(axis=1), 1.0)
+    pts[500] = [0.25, 0.1]
+    with pytest.raises(ZeroDivisionError):
+        tree.compute_barycentric_weights(pts, tolerance=0.0)
+    i, w = tree.compute_barycentric_weights(pts)  # default tolerance: the on-edge interpolation takes over
+    assert i[500] == 0 and np.array_equal(w[500], [0.0, 0.6, 0.4, 0.0])
+    assert np.array_equal(tree.locate_points(pts, tolerance=0.0), oracle.CellTree2d(v, f, -1).locate_points(pts, 0.0))
+    v3 = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0], [0.0, 1.0]])
+    f3 = np.array([[0, 1, 2], [0, 1, 3]])
+    i3, w3 = pkg.CellTree2d(v3, f3, -1).compute_barycentric_weights(np.array([[0.5, 0.0], [0.2, 0.2]]))
+    assert i3.tolist() == [0, 1] and np.isnan(w3[0]).all() and np.allclose(w3[1], [0.6, 0.2, 0.2], rtol=1e-15)
