@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
 #ifndef CT_EXP2
 #define CT_EXP2 0
 #endif
+#ifndef CT_WEIGHTS_MINB
+#define CT_WEIGHTS_MINB 4  // the same with fused barycentric weights (C2, 100 M points: 2 -> 11.9 ms, 3 -> 11.1, 4 -> 10.6)
+#endif
 #ifndef CT_TILE_MINB
 #define CT_TILE_MINB 4  // blocks per SM of the 3- and 4-vertex kernels (64 registers)
 #endif
@@ -290,7 +293,7 @@ static int launch_locate_points_binned(const TreeView &v, const TileInput &in, i
         return CT_OK;
     };
     if (weights) {
-        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, 2, false>, k_locate_points_binned<MAXV, true, 2, true>));
+        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), false>, k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), true>));
     } else if (MAXV <= 4)
         CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB, false>, k_locate_points_binned<MAXV, false, CT_TILE_MINB, true>));
     else
