@@ -174,27 +174,66 @@ CT_DEV double div_exact(double a, double b) {
     return a / b;
 }
 
+// One edge v0 -> v1 of point_in_polygon_or_on_edge (geometry_utils.py:203-220): U = v0 - p is carried from the previous
+// edge, V = v1 - p becomes the next U.  Returns true when the point is accepted on this edge; flips `c` on a crossing.
+CT_DEV bool pip_edge(P2 p, P2 v0, P2 v1, P2 U, P2 &V, double tolerance, bool &c) {
+    V = to_vector(p, v1);
+    const double A = cross_product(U, V);
+    const P2 W = to_vector(v0, v1);
+    if (within_perpendicular_distance(A, W, tolerance) && in_bounds(p, v0, v1)) return true;
+    if (((v0.y > p.y) != (v1.y > p.y)) && (p.x < (div_exact((v1.x - v0.x) * (p.y - v0.y), (v1.y - v0.y)) + v0.x))) c = !c;
+    return false;
+}
+
 // geometry_utils.py:195-223 -- crossing-number test with tolerance-based acceptance on the boundary.
+//
+// Two facts about the reference's loop let the 3- and 4-vertex forms below run without its two data-dependent parts:
+//  * its result is (some edge accepts the point) OR (the number of crossings is odd): both are independent of the order in
+//    which the edges are visited, and every edge's arithmetic only involves its own two vertices and the point;
+//  * an edge of zero length (`if v1 == v0: continue`) changes nothing even when it is not skipped: U and V are then the same
+//    vector (up to the sign of a zero), A = U.x * V.y - U.y * V.x is a zero, W is a zero vector, so the acceptance test reads
+//    0 < (tolerance * 0) * tolerance -- false, also for an infinite or NaN tolerance -- and the crossing test reads
+//    (v.y > p.y) != (v.y > p.y), false; where v1 and v0 differ in the sign of a zero, later comparisons cannot tell.
+// So a triangle stored in a four-vertex row is walked as the quad (v0, v1, v2, v0): its edges are the triangle's three
+// plus the zero-length edge v0 -> v0, and no vertex has to be picked by a run-time index.
 template <int MAXV>
 CT_DEV bool point_in_polygon_or_on_edge(P2 p, const Poly<MAXV> &poly, double tolerance) {
-    const int length = poly.n;
-    P2 v0 = pget(poly, length - 1);
-    P2 U = to_vector(p, v0);
-    bool c = false;
-#pragma unroll
-    for (int i = 0; i < MAXV; i++) {
-        if (i >= length) break;
-        P2 v1{poly.x[i], poly.y[i]};
-        if (v1.x == v0.x && v1.y == v0.y) continue;
-        P2 V = to_vector(p, v1);
-        double A = cross_product(U, V);
-        P2 W = to_vector(v0, v1);
-        if (within_perpendicular_distance(A, W, tolerance) && in_bounds(p, v0, v1)) return true;
-        if (((v0.y > p.y) != (v1.y > p.y)) && (p.x < (div_exact((v1.x - v0.x) * (p.y - v0.y), (v1.y - v0.y)) + v0.x))) c = !c;
-        v0 = v1;
+    if constexpr (MAXV == 3 || MAXV == 4) {
+        const P2 a{poly.x[0], poly.y[0]}, b{poly.x[1], poly.y[1]}, d{poly.x[2], poly.y[2]};
+        P2 last = d;
+        if constexpr (MAXV == 4) {
+            if (poly.n == 4) last = P2{poly.x[3], poly.y[3]};
+            else last = a;  // triangle in a quad row: closing edge d -> a, then the zero-length edge a -> a
+        }
+        bool c = false;
+        P2 U = to_vector(p, last), V;
+        if (pip_edge(p, last, a, U, V, tolerance, c)) return true;
         U = V;
+        if (pip_edge(p, a, b, U, V, tolerance, c)) return true;
+        U = V;
+        if (pip_edge(p, b, d, U, V, tolerance, c)) return true;
+        if constexpr (MAXV == 4) {
+            U = V;
+            if (pip_edge(p, d, last, U, V, tolerance, c)) return true;
+        }
+        return c;
+    } else {
+        const int length = poly.n;
+        P2 v0 = pget(poly, length - 1);
+        P2 U = to_vector(p, v0);
+        bool c = false;
+#pragma unroll
+        for (int i = 0; i < MAXV; i++) {
+            if (i >= length) break;
+            P2 v1{poly.x[i], poly.y[i]};
+            if (v1.x == v0.x && v1.y == v0.y) continue;
+            P2 V;
+            if (pip_edge(p, v0, v1, U, V, tolerance, c)) return true;
+            v0 = v1;
+            U = V;
+        }
+        return c;
     }
-    return c;
 }
 
 CT_DEV bool point_on_edge(P2 p, P2 v0, P2 v1, double tolerance) {  // geometry_utils.py:226-238
