@@ -136,6 +136,17 @@ CT_DEV int4 cursor_leaf(const Cursor &c) {  // {ptr, size, id0, id1}
     const long long a = __double_as_longlong(c.plane.x), b = __double_as_longlong(c.plane.y);
     return make_int4((int)(a & 0xffffffffLL), (int)(a >> 32), (int)(b & 0xffffffffLL), (int)(b >> 32));
 }
+// Every element of a leaf in its order: the first two ids travel with the node (no run-time selection among them: a
+// `k == 0 ? z : k == 1 ? w : load` chain inside a loop was 16 % of the box walk's instructions, at five active lanes), the
+// rest come from bb_indices.  `visit` returns true to stop early.
+template <typename Visit>
+CT_DEV bool for_each_leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices, Visit visit) {
+    if (leaf.y > 0 && visit(leaf.z)) return true;
+    if (leaf.y > 1 && visit(leaf.w)) return true;
+    for (int k = 2; k < leaf.y; k++)
+        if (visit(__ldg(bb_indices + leaf.x + k))) return true;
+    return false;
+}
 // k-th element of a leaf: the first two ids travel with the node, the rest come from bb_indices
 CT_DEV int leaf_element(const int4 &leaf, const int32_t *__restrict__ bb_indices, int k) {
     return k == 0 ? leaf.z : (k == 1 ? leaf.w : __ldg(bb_indices + leaf.x + k));
@@ -211,13 +222,16 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe 
             }
         }
         const int4 leaf = cursor_leaf(c);
-        for (int k = 0; k < leaf.y; k++) {
-            int bbox_index = leaf_element(leaf, t.bb_indices, k);
-            Poly<MAXV> poly;
-            pr.cell();
-            load_tree_polygon<MAXV>(t, bbox_index, poly);
-            if (point_in_polygon_or_on_edge(p, poly, tolerance)) return bbox_index;
-        }
+        int found = -1;
+        if (for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
+                Poly<MAXV> poly;
+                pr.cell();
+                load_tree_polygon<MAXV>(t, bbox_index, poly);
+                if (!point_in_polygon_or_on_edge(p, poly, tolerance)) return false;
+                found = bbox_index;
+                return true;
+            }))
+            return found;
         if (stack.empty()) return -1;
         enter(stack.pop(t));
     }
@@ -252,12 +266,15 @@ CT_DEV int locate_point_on_edge(const TreeView &t, P2 p, double tolerance) {
             }
         }
         const int4 leaf = cursor_leaf(c);
-        for (int k = 0; k < leaf.y; k++) {
-            int bbox_index = leaf_element(leaf, t.bb_indices, k);
-            double2 v0 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
-            double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
-            if (point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return bbox_index;
-        }
+        int found = -1;
+        if (for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
+                double2 v0 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index);
+                double2 v1 = __ldg(t.elem_xy + 2 * (int64_t)bbox_index + 1);
+                if (!point_on_edge(p, P2{v0.x, v0.y}, P2{v1.x, v1.y}, tolerance)) return false;
+                found = bbox_index;
+                return true;
+            }))
+            return found;
         if (stack.empty()) return -1;
         cursor_enter(c, base, stack.pop(t));
     }
@@ -284,14 +301,14 @@ CT_DEV int locate_box(const TreeView &t, const Box4 &box, Emit emit) {
         bool pop;
         if (cursor_is_leaf(c)) {
             const int4 leaf = cursor_leaf(c);
-            for (int k = 0; k < leaf.y; k++) {
-                int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
                 Box4 leaf_box = load_box(t.bb_coords, bbox_index);
                 if (boxes_intersect(box, leaf_box)) {
                     emit(count, bbox_index);
                     count++;
                 }
-            }
+                return false;
+            });
             pop = true;
         } else {
             const bool dim = cursor_dim(c);
@@ -405,14 +422,14 @@ CT_DEV int locate_edge(const TreeView &t, P2 a, P2 b, Emit emit) {
         bool pop;
         if (cursor_is_leaf(cur)) {
             const int4 leaf = cursor_leaf(cur);
-            for (int k = 0; k < leaf.y; k++) {
-                int bbox_index = leaf_element(leaf, t.bb_indices, k);
+            for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
                 P2 c, d;
                 if (edge_cell_intersect<MAXV>(t, bbox_index, a, b, c, d)) {
                     emit(count, bbox_index, c, d);
                     count++;
                 }
-            }
+                return false;
+            });
             pop = true;
         } else {
             bool left, right;
