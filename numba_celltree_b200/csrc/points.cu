@@ -142,6 +142,8 @@ struct TileInput {
     const uint32_t *perm;        // else: query indices in bin order ...
     const double2 *points;       // ... into the caller's points
     BinGrid grid;
+    const uint32_t *slab_fill;   // slab bins (binning.cuh): tile b is bin b, records [b * SLAB, b * SLAB + min(fill[b], SLAB)) ...
+    SlabPlan plan;               // ... sorted by the key relative to the bin's first key
 };
 
 CT_DEV double2 load_point_once(const double2 *p) {
@@ -155,8 +157,17 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
     k_locate_points_binned(TreeView t, TileInput in, int64_t n, double tolerance, uint2 *__restrict__ pairs,
                            uint32_t *__restrict__ window_cursor, int64_t *__restrict__ out, double *__restrict__ weights) {
     __shared__ TileShared sh;
+    const bool slabs = !GATHER && in.slab_fill != nullptr;
     const int64_t base = (int64_t)blockIdx.x * TILE;
-    const int m = (int)((n - base) < TILE ? (n - base) : TILE);
+    int m;
+    if (slabs) {
+        const uint32_t fill = __ldg(in.slab_fill + blockIdx.x);
+        m = fill < (uint32_t)SLAB ? (int)fill : SLAB;
+        if (m == 0) return;
+    } else {
+        m = (int)((n - base) < TILE ? (n - base) : TILE);
+    }
+    static_assert(SLAB == TILE, "a slab is one tile");
     const PointRecord *tile = in.records + base;
     const uint32_t *tile_perm = in.perm + base;
     if (threadIdx.x == 0) {
@@ -193,26 +204,39 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
             key24[k] = j < m ? __ldg(&tile[j].key) : 0xffffffffu;
         }
     }
+    uint32_t key0, span;
+    if (slabs) {
+        // one bin: keys relative to the bin's first key, cut down to the plan's sort bits
+        span = (1u << in.plan.sort_bits) - 1u;
+        key0 = 0;
+        const uint32_t first_key = slab_first_key(blockIdx.x, in.plan.bins);
 #pragma unroll
-    for (int k = 0; k < TILE_ITEMS; k++) {
-        const int j = k * TILE_THREADS + threadIdx.x;
-        if (j < m) {
-            lo = key24[k] < lo ? key24[k] : lo;
-            hi = key24[k] > hi ? key24[k] : hi;
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const uint32_t rel = (key24[k] - first_key) >> in.plan.shift;
+            key24[k] = rel < span ? rel : span;
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            if (j < m) {
+                lo = key24[k] < lo ? key24[k] : lo;
+                hi = key24[k] > hi ? key24[k] : hi;
+            }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&sh.lo, lo);
+            atomicMax(&sh.hi, hi);
+        }
+        __syncthreads();
+        // key relative to the tile's first bin, saturating (a tile that spans more than 256 bins is too sparse for the
+        // order of its far end to matter)
+        key0 = (sh.lo >> FINE_BITS) << FINE_BITS;
+        span = sh.hi - key0;
+        span = span < 0xffffu ? span : 0xffffu;
     }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&sh.lo, lo);
-        atomicMax(&sh.hi, hi);
-    }
-    __syncthreads();
-    // key relative to the tile's first bin, saturating (a tile that spans more than 256 bins is too sparse for the
-    // order of its far end to matter)
-    const uint32_t key0 = (sh.lo >> FINE_BITS) << FINE_BITS;
-    uint32_t span = sh.hi - key0;
-    span = span < 0xffffu ? span : 0xffffu;
     uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
 #pragma unroll
     for (int k = 0; k < TILE_ITEMS; k++) {
@@ -283,10 +307,51 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
     }
 }
 
+// The points that found their bin's slab full (binning.cuh): walked in arrival order by a grid that covers the machine
+// once, however many there are (the count stays on the device).
+template <int MAXV, bool WEIGHTS>
+__global__ void __launch_bounds__(BLOCK) k_locate_points_overflow(TreeView t, const double2 *__restrict__ points, const uint32_t *__restrict__ list,
+                                                                  const uint32_t *__restrict__ count, double tolerance,
+                                                                  uint2 *__restrict__ pairs, uint32_t *__restrict__ window_cursor,
+                                                                  int64_t *__restrict__ out, double *__restrict__ weights) {
+    const uint32_t n = __ldg(count);
+    for (uint32_t k = blockIdx.x * BLOCK + threadIdx.x; k < n; k += gridDim.x * BLOCK) {
+        const uint32_t index = __ldg(list + k);
+        const double2 pt = load_point_once(points + index);
+        const P2 p{pt.x, pt.y};
+        int found;
+        if constexpr (MAXV == 0) found = locate_point_on_edge(t, p, tolerance);
+        else found = locate_point<MAXV>(t, p, tolerance);
+        if (pairs) {
+            const uint32_t slot = atomicAdd(window_cursor + (index >> WINDOW_BITS), 1u);
+            pairs[((int64_t)(index >> WINDOW_BITS) << WINDOW_BITS) + slot] = make_uint2(index, (uint32_t)found);
+        } else {
+            out[index] = (int64_t)found;
+        }
+        if constexpr (WEIGHTS) write_weights<MAXV, WEIGHTS>(t, found, p, tolerance, weights + (int64_t)index * t.M);
+    }
+}
+
+template <int MAXV>
+static int launch_locate_points_overflow(const TreeView &v, const double2 *pts, const uint32_t *list, const uint32_t *count, double tol,
+                                         uint2 *pairs, uint32_t *window_cursor, int64_t *out, double *weights, cudaStream_t s) {
+    int device = 0, sms = 0;
+    CT_CUDA(cudaGetDevice(&device));
+    CT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = sms * 8;
+    if (weights) {
+        if constexpr (MAXV > 0) k_locate_points_overflow<MAXV, true><<<grid, BLOCK, 0, s>>>(v, pts, list, count, tol, pairs, window_cursor, out, weights);
+    } else {
+        k_locate_points_overflow<MAXV, false><<<grid, BLOCK, 0, s>>>(v, pts, list, count, tol, pairs, window_cursor, out, weights);
+    }
+    CT_LAUNCH_CHECK();
+    return CT_OK;
+}
+
 template <int MAXV>
 static int launch_locate_points_binned(const TreeView &v, const TileInput &in, int64_t n, double tol, uint2 *pairs,
                                        uint32_t *window_cursor, int64_t *out, double *weights, cudaStream_t s) {
-    const int grid = grid_for(n, TILE);
+    const int grid = in.slab_fill ? (int)in.plan.bins : grid_for(n, TILE);
     auto launch = [&](auto binned, auto gathered) -> int {
         if (in.records) binned<<<grid, TILE_THREADS, 0, s>>>(v, in, n, tol, pairs, window_cursor, out, weights);
         else gathered<<<grid, TILE_THREADS, 0, s>>>(v, in, n, tol, pairs, window_cursor, out, weights);
@@ -359,14 +424,15 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
         if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
         return status == CT_OK ? deep.finish() : status;
     }
-    // Execution order (CELLTREE_ORDER, measured on C2 with 100 M points, step in ms): "bins" (default) moves the points into
-    // 16-bit Z-order bins (binning.cuh): 7.25; "sort" radix-sorts (bin, index) pairs and lets the tiles gather: 7.6 (the
-    // sort is 1.3 ms cheaper, the gathering traversal 1.7 ms dearer); "morton" is round 1's full 24-bit sort of (key, index)
-    // pairs with one gathered query per thread: 7.8 with the window queues.
+    // Execution order (CELLTREE_ORDER, measured on C2 with 100 M points): "slabs" (default) appends every point to the slab
+    // of its Z-order bin, no counting pass (binning.cuh); "bins" counts first and packs the bins densely (+0.7 ms); "sort"
+    // radix-sorts (bin, index) pairs and lets the tiles gather (the sort is 1.3 ms cheaper than "bins", the gathering
+    // traversal 1.7 ms dearer); "morton" is round 1's full 24-bit sort of (key, index) pairs with one gathered query per
+    // thread (+0.6 ms against "bins" with the window queues).
     static int order_mode = -1;
     if (order_mode < 0) {
         const char *e = getenv("CELLTREE_ORDER");
-        order_mode = (e && e[0] == 's') ? 1 : ((e && e[0] == 'm') ? 2 : 0);
+        order_mode = !e ? 3 : (e[0] == 'b' ? 0 : (e[0] == 's' && e[1] == 'o' ? 1 : (e[0] == 'm' ? 2 : 3)));
     }
     if (order_mode == 2 && tree->kind == CT_KIND_FACES) {
         // full Z-order sort of (key, index) pairs, one query per thread with the point gathered through the permutation
@@ -398,8 +464,15 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
     }
     PointBins bins;
     BinSort sorted;
-    TileInput in{nullptr, nullptr, pts, BinGrid{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy}};
-    if (order_mode == 0) {
+    PointSlabs slabs;
+    TileInput in{nullptr, nullptr, pts, BinGrid{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy}, nullptr, SlabPlan{}};
+    if (order_mode == 3 && n > ((int64_t)400 << 20)) order_mode = 0;  // the slabs of that many points: too much memory
+    if (order_mode == 3) {
+        CT_CHECK(slabs.build(tree, pts, n, s));
+        in.records = slabs.records.p;
+        in.slab_fill = slabs.cursor.p;
+        in.plan = slabs.plan;
+    } else if (order_mode == 0) {
         CT_CHECK(bins.build(tree, pts, n, s));
         in.records = bins.records.p;
     } else {
@@ -423,6 +496,14 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
     else if (tree->M == 4) status = launch_locate_points_binned<4>(v, in, n, tol, pairs.p, wc, out, weights, s);
     else if (tree->M <= 8) status = launch_locate_points_binned<8>(v, in, n, tol, pairs.p, wc, out, weights, s);
     else status = launch_locate_points_binned<32>(v, in, n, tol, pairs.p, wc, out, weights, s);
+    if (status == CT_OK && in.slab_fill) {
+        const uint32_t *list = slabs.overflow.p, *count = slabs.overflow_count();
+        if (tree->kind == CT_KIND_EDGES) status = launch_locate_points_overflow<0>(v, pts, list, count, tol, pairs.p, wc, out, nullptr, s);
+        else if (tree->M == 3) status = launch_locate_points_overflow<3>(v, pts, list, count, tol, pairs.p, wc, out, weights, s);
+        else if (tree->M == 4) status = launch_locate_points_overflow<4>(v, pts, list, count, tol, pairs.p, wc, out, weights, s);
+        else if (tree->M <= 8) status = launch_locate_points_overflow<8>(v, pts, list, count, tol, pairs.p, wc, out, weights, s);
+        else status = launch_locate_points_overflow<32>(v, pts, list, count, tol, pairs.p, wc, out, weights, s);
+    }
     if (ev) CT_CUDA(cudaEventRecord(ev->done, s));
     if (status == CT_OK && queued) {
         CT_CUDA(cudaFuncSetAttribute(k_windows_to_out, cudaFuncAttributeMaxDynamicSharedMemorySize, WINDOW * (int)sizeof(int32_t)));

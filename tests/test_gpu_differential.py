@@ -119,6 +119,23 @@ def test_morton_ordering_is_invisible(pkg, delaunay_pair):
         assert np.array_equal(w, results[0][1])
 
 
+def test_crowded_query_sets(pkg, delaunay_pair):
+    """Points crowded into a few bins of the execution order (slabs that overflow), identical points, sorted points:
+    the order is an execution detail, the answers are the oracle's."""
+    tree, ref, _, _ = delaunay_pair
+    rng = np.random.default_rng(12)
+    n = 1_200_000
+    crowded = np.column_stack((rng.normal(0.37, 0.002, n), rng.normal(0.61, 0.001, n)))  # nearly all in a handful of bins
+    crowded[::1000] = rng.uniform(-0.1, 1.1, (len(crowded[::1000]), 2))
+    same = np.full((400_000, 2), 0.25)
+    same[::3] = [0.75, 0.5]
+    grid = np.stack(np.meshgrid(np.linspace(0, 1, 700), np.linspace(0, 1, 600), indexing="xy"), axis=-1).reshape(-1, 2)  # sorted rows
+    for pts in (crowded, same, grid):
+        i, w = tree.compute_barycentric_weights(pts)
+        ri, rw = ref.compute_barycentric_weights(pts)
+        assert np.array_equal(i, ri) and np.array_equal(w, rw)
+
+
 def test_device_resident_inputs_match_host(delaunay_pair):
     torch = pytest.importorskip("torch")
     tree, _, _, faces = delaunay_pair
