@@ -276,7 +276,7 @@ constexpr int SLAB = 2048;
 struct SlabPlan {
     uint32_t bins;  // any number, not only powers of two: bin = key24 * bins >> 24 maps the Z-order curve onto them in order
     int shift;      // a tile is sorted by (key24 - first key of its bin) >> shift ...
-    int sort_bits;  // ... which has this many bits (<= 10: a thousand places for at most 2048 points)
+    int sort_bits;  // ... which has this many bits (<= 8: two 4-bit passes of the block sort; 256 places for at most 2048 points)
     static SlabPlan make(int64_t n) {
         SlabPlan p;
         const int64_t target = SLAB * 7 / 8;  // mean points per bin: 1792 +- 42 for uniform points, 6 deviations below the slab
@@ -287,7 +287,7 @@ struct SlabPlan {
         const uint32_t range = (uint32_t)(((uint64_t)1 << 24) / p.bins) + 2;  // keys per bin, at most
         int bits = 1;
         while (bits < 24 && (1u << bits) < range) bits++;
-        p.sort_bits = bits < 10 ? bits : 10;
+        p.sort_bits = bits < 8 ? bits : 8;
         p.shift = bits - p.sort_bits;
         return p;
     }

@@ -30,8 +30,11 @@ constexpr int QUEUE_CAP = 64;  // per warp: a step adds at most 32 candidates, a
 
 // 120 registers, 4 blocks of 128 threads per SM.  Capping the registers for more resident warps loses: C4 call 40.9 ms
 // as is, 42.1 ms at 96 registers (5 blocks, 124 bytes spilled), 50.5 ms at 80 registers (6 blocks, 178 bytes spilled).
+#ifndef CT_EDGES_MINB
+#define CT_EDGES_MINB 4
+#endif
 template <int MAXV>
-__global__ void __launch_bounds__(BLOCK) k_edges_cooperative(TreeView t, const double *__restrict__ edges, int64_t n,
+__global__ void __launch_bounds__(BLOCK, CT_EDGES_MINB) k_edges_cooperative(TreeView t, const double *__restrict__ edges, int64_t n,
                                                              int32_t *__restrict__ counts, const uint32_t *__restrict__ perm,
                                                              HitLog log) {
     constexpr int WARPS = BLOCK / 32;
