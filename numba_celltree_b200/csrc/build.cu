@@ -308,6 +308,9 @@ struct BuildState {
     // Signed-zero mode (only when a bounding box holds -0.0, see k_zero_first): position of the first element whose
     // value equals a zero extreme, per active slot (range) and per (slot, bucket); nullptr otherwise
     int32_t *a_minpos, *a_maxpos, *b_minpos, *b_maxpos;
+    // At most four buckets (the default): the stable partition's ranks come from per-block bucket counts (written by
+    // k_bucket) instead of a scan over all positions, see k_scatter4.  nullptr otherwise.
+    uint4 *block_counts;
 };
 
 // The reference takes extremes with strict comparisons in slice order (get_bounds, creation.py:153-171: `value < Rmin`,
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
         __syncthreads();
     }
     int slot = pos < n ? st.seg[pos] : -1;
+    int my_bucket = -1;
     if (slot >= 0) {
         int node = st.active[slot];
         int dim = st.n_dim[node];
@@ -450,6 +454,7 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
             k = nb - 1;
         }
         st.bkt[pos] = (uint16_t)k;
+        my_bucket = k;
         if (st.a_minpos) vmin = unsigned_zero(vmin), vmax = unsigned_zero(vmax);
         unsigned long long emin = (vmin == vmin) ? enc(vmin) : enc(FLOAT_MAX);
         unsigned long long emax = (vmax == vmax) ? enc(vmax) : enc(FLOAT_MIN);
@@ -474,6 +479,11 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
                 atomicMax(st.b_max + o, s_bmax[k]);
             }
         }
+    }
+    if (st.block_counts) {  // how many elements of this block went to each of the (at most four) buckets
+        const int c0 = __syncthreads_count(my_bucket == 0), c1 = __syncthreads_count(my_bucket == 1);
+        const int c2 = __syncthreads_count(my_bucket == 2), c3 = __syncthreads_count(my_bucket == 3);
+        if (threadIdx.x == 0) st.block_counts[blockIdx.x] = make_uint4(c0, c1, c2, c3);
     }
 }
 
@@ -681,6 +691,62 @@ __global__ void __launch_bounds__(BB) k_scatter(BuildState st, const int32_t *__
     int node = st.active[slot];
     int k = st.bkt[pos];
     int np = st.n_ptr[node] + st.b_start[(int64_t)slot * st.nb + k] + rank[pos];
+    idx_out[np] = idx_in[pos];
+    seg_out[np] = (np < st.split_pos[slot]) ? st.next_left[slot] : st.next_right[slot];
+}
+
+// ---- at most four buckets: ranks without the scan over all positions -------------------------------------------------
+// The rank of an element among the same-bucket elements of its node that precede it is S(pos) - S(ptr of its node), where
+// S(pos)[k] counts the bucket-k elements at positions < pos.  S(pos) = (exclusive scan over the per-block counts that
+// k_bucket left)[block of pos] + (bucket-k elements before pos within its block): the first is a scan over n / 256 values
+// instead of n, the second four ballots per warp.  One pass notes S at every node's first position, the scatter pass
+// recomputes S for its own position and subtracts.
+__device__ __forceinline__ uint4 block_exclusive4(int bucket, uint4 (*s_warp)[BB / 32]) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned m0 = __ballot_sync(0xffffffffu, bucket == 0), m1 = __ballot_sync(0xffffffffu, bucket == 1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, bucket == 2), m3 = __ballot_sync(0xffffffffu, bucket == 3);
+    if (lane == 0) (*s_warp)[warp] = make_uint4(__popc(m0), __popc(m1), __popc(m2), __popc(m3));
+    __syncthreads();
+    uint4 r = make_uint4(__popc(m0 & lt), __popc(m1 & lt), __popc(m2 & lt), __popc(m3 & lt));
+    for (unsigned w = 0; w < warp; w++) {
+        const uint4 t = (*s_warp)[w];
+        r.x += t.x, r.y += t.y, r.z += t.z, r.w += t.w;
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(BB) k_node_base4(BuildState st, const uint4 *__restrict__ block_prefix, int64_t n, uint4 *__restrict__ node_base) {
+    __shared__ uint4 s_warp[BB / 32];
+    const int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    const int slot = pos < n ? st.seg[pos] : -1;
+    const int bucket = slot >= 0 ? (int)st.bkt[pos] : -1;
+    const uint4 in_block = block_exclusive4(bucket, &s_warp);
+    if (slot >= 0 && pos == st.n_ptr[st.active[slot]]) {
+        const uint4 b = block_prefix[blockIdx.x];
+        node_base[slot] = make_uint4(b.x + in_block.x, b.y + in_block.y, b.z + in_block.z, b.w + in_block.w);
+    }
+}
+
+__global__ void __launch_bounds__(BB) k_scatter4(BuildState st, const int32_t *__restrict__ idx_in, const uint4 *__restrict__ block_prefix,
+                                                const uint4 *__restrict__ node_base, int64_t n, int32_t *__restrict__ idx_out,
+                                                int32_t *__restrict__ seg_out) {
+    __shared__ uint4 s_warp[BB / 32];
+    const int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
+    const int slot = pos < n ? st.seg[pos] : -1;
+    const int k = slot >= 0 ? (int)st.bkt[pos] : -1;
+    const uint4 in_block = block_exclusive4(k, &s_warp);
+    if (pos >= n) return;
+    if (slot < 0) {
+        idx_out[pos] = idx_in[pos];
+        seg_out[pos] = -1;
+        return;
+    }
+    const uint4 b = block_prefix[blockIdx.x], base = node_base[slot];
+    const unsigned rank = pick4(make_uint4(b.x + in_block.x, b.y + in_block.y, b.z + in_block.z, b.w + in_block.w), k) - pick4(base, k);
+    const int node = st.active[slot];
+    const int np = st.n_ptr[node] + st.b_start[(int64_t)slot * st.nb + k] + (int)rank;
     idx_out[np] = idx_in[pos];
     seg_out[np] = (np < st.split_pos[slot]) ? st.next_left[slot] : st.next_right[slot];
 }
@@ -1030,9 +1096,11 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     CT_CHECK(idx_b.alloc(n, s));
     CT_CHECK(seg_a.alloc(n, s));
     CT_CHECK(seg_b.alloc(n, s));
-    CT_CHECK(rank.alloc(n, s));
     CT_CHECK(bkt.alloc(n, s));
-    CT_CHECK(scan.alloc(n, s));
+    if (nb > 4) {  // the scan over all positions and the ranks it yields: only with more than four buckets (see k_scatter4)
+        CT_CHECK(rank.alloc(n, s));
+        CT_CHECK(scan.alloc(n, s));
+    }
     CT_CHECK(n_ptr.alloc(cap_nodes, s));
     CT_CHECK(n_size.alloc(cap_nodes, s));
     CT_CHECK(n_child.alloc(cap_nodes, s));
@@ -1051,6 +1119,19 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     CT_CHECK(b_min.alloc(cap_buckets, s));
     CT_CHECK(b_max.alloc(cap_buckets, s));
     CT_CHECK(b_start.alloc(cap_buckets, s));
+    // at most four buckets: per-block bucket counts, their scan, and the scan value at every active node's first position
+    const bool few_buckets = nb <= 4;
+    const int64_t n_blocks = grid_for(n, BB);
+    Scratch<uint4> block_counts, block_prefix, node_base;
+    Scratch<char> block_scan_tmp;
+    size_t block_scan_bytes = 0;
+    if (few_buckets) {
+        CT_CHECK(block_counts.alloc(n_blocks, s));
+        CT_CHECK(block_prefix.alloc(n_blocks, s));
+        CT_CHECK(node_base.alloc(cap_active, s));
+        CT_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, block_scan_bytes, block_counts.p, block_prefix.p, Add4(), make_uint4(0, 0, 0, 0), n_blocks, s));
+        CT_CHECK(block_scan_tmp.alloc(block_scan_bytes, s));
+    }
     Scratch<int32_t> a_minpos, a_maxpos, b_minpos, b_maxpos;  // signed-zero mode only
     bool signed_zero = false;
     CT_CHECK(next_left.alloc(cap_active, s));
@@ -1059,7 +1140,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     CT_CHECK(counters.alloc(4, s));
 
     size_t scan_bytes = 0;
-    {
+    if (nb > 4) {
         OneHot4 oh{seg_a.p, bkt.p, 0};
         auto in = cub::TransformInputIterator<uint4, OneHot4, cub::CountingInputIterator<int64_t>>(cub::CountingInputIterator<int64_t>(0), oh);
         CT_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, scan_bytes, in, scan.p, Add4(), make_uint4(0, 0, 0, 0), n, s));
@@ -1111,6 +1192,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     st.next_left = next_left.p; st.next_right = next_right.p; st.split_pos = split_pos.p;
     st.counters = counters.p;
     st.a_minpos = a_minpos.p; st.a_maxpos = a_maxpos.p; st.b_minpos = b_minpos.p; st.b_maxpos = b_maxpos.p;
+    st.block_counts = block_counts.p;
     st.nb = nb; st.cpl = cpl;
 
     int32_t *idx_cur = idx_a.p, *idx_nxt = idx_b.p, *seg_cur = seg_a.p, *seg_nxt = seg_b.p, *act_cur = act_a.p, *act_nxt = act_b.p;
@@ -1152,17 +1234,27 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
         }
         k_decide<<<grid_for(n_active, 128), 128, 0, s>>>(st, n_active);
         CT_LAUNCH_CHECK();
-        for (int g = 0; g < n_groups; g++) {
-            OneHot4 oh{seg_cur, bkt.p, g};
-            auto in = cub::TransformInputIterator<uint4, OneHot4, cub::CountingInputIterator<int64_t>>(cub::CountingInputIterator<int64_t>(0), oh);
-            size_t bytes = scan_bytes;
-            CT_CUDA(cub::DeviceScan::ExclusiveScan(scan_tmp.p, bytes, in, scan.p, Add4(), make_uint4(0, 0, 0, 0), n, s));
+        if (few_buckets) {
+            size_t bytes = block_scan_bytes;
+            CT_CUDA(cub::DeviceScan::ExclusiveScan(block_scan_tmp.p, bytes, block_counts.p, block_prefix.p, Add4(), make_uint4(0, 0, 0, 0), n_blocks, s));
             count_launch(2);
-            k_rank<<<grid_for(n, BB), BB, 0, s>>>(st, scan.p, g, n, rank.p);
+            k_node_base4<<<grid_for(n, BB), BB, 0, s>>>(st, block_prefix.p, n, node_base.p);
+            CT_LAUNCH_CHECK();
+            k_scatter4<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, block_prefix.p, node_base.p, n, idx_nxt, seg_nxt);
+            CT_LAUNCH_CHECK();
+        } else {
+            for (int g = 0; g < n_groups; g++) {
+                OneHot4 oh{seg_cur, bkt.p, g};
+                auto in = cub::TransformInputIterator<uint4, OneHot4, cub::CountingInputIterator<int64_t>>(cub::CountingInputIterator<int64_t>(0), oh);
+                size_t bytes = scan_bytes;
+                CT_CUDA(cub::DeviceScan::ExclusiveScan(scan_tmp.p, bytes, in, scan.p, Add4(), make_uint4(0, 0, 0, 0), n, s));
+                count_launch(2);
+                k_rank<<<grid_for(n, BB), BB, 0, s>>>(st, scan.p, g, n, rank.p);
+                CT_LAUNCH_CHECK();
+            }
+            k_scatter<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, rank.p, n, idx_nxt, seg_nxt);
             CT_LAUNCH_CHECK();
         }
-        k_scatter<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, rank.p, n, idx_nxt, seg_nxt);
-        CT_LAUNCH_CHECK();
         int32_t h[4];
         CT_CUDA(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
         CT_CUDA(cudaStreamSynchronize(s));
