@@ -311,6 +311,7 @@ struct BuildState {
     // At most four buckets (the default): the stable partition's ranks come from per-block bucket counts (written by
     // k_bucket) instead of a scan over all positions, see k_scatter4.  nullptr otherwise.
     uint4 *block_counts;
+    uint4 *node_inblock;  // per active slot: bucket counts within its first position's block, before that position
 };
 
 // The reference takes extremes with strict comparisons in slice order (get_bounds, creation.py:153-171: `value < Rmin`,
@@ -388,6 +389,23 @@ __global__ void __launch_bounds__(BB) k_range(BuildState st, const int32_t *__re
         atomicMin(st.a_min + slot_first, emin);
         atomicMax(st.a_max + slot_first, emax);
     }
+}
+
+// bucket-k elements among the earlier threads of the block, k = 0..3 (used by the at-most-four-buckets partition below)
+__device__ __forceinline__ uint4 block_exclusive4(int bucket, uint4 (*s_warp)[BB / 32]) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned m0 = __ballot_sync(0xffffffffu, bucket == 0), m1 = __ballot_sync(0xffffffffu, bucket == 1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, bucket == 2), m3 = __ballot_sync(0xffffffffu, bucket == 3);
+    if (lane == 0) (*s_warp)[warp] = make_uint4(__popc(m0), __popc(m1), __popc(m2), __popc(m3));
+    __syncthreads();
+    uint4 r = make_uint4(__popc(m0 & lt), __popc(m1 & lt), __popc(m2 & lt), __popc(m3 & lt));
+    for (unsigned w = 0; w < warp; w++) {
+        const uint4 t = (*s_warp)[w];
+        r.x += t.x, r.y += t.y, r.z += t.z, r.w += t.w;
+    }
+    __syncthreads();
+    return r;
 }
 
 constexpr int SMEM_BUCKETS = 64;
@@ -484,6 +502,9 @@ __global__ void __launch_bounds__(BB) k_bucket(BuildState st, const int32_t *__r
         const int c0 = __syncthreads_count(my_bucket == 0), c1 = __syncthreads_count(my_bucket == 1);
         const int c2 = __syncthreads_count(my_bucket == 2), c3 = __syncthreads_count(my_bucket == 3);
         if (threadIdx.x == 0) st.block_counts[blockIdx.x] = make_uint4(c0, c1, c2, c3);
+        __shared__ uint4 s_warp4[BB / 32];
+        const uint4 before = block_exclusive4(my_bucket, &s_warp4);
+        if (slot >= 0 && pos == st.n_ptr[st.active[slot]]) st.node_inblock[slot] = before;
     }
 }
 
@@ -699,36 +720,8 @@ __global__ void __launch_bounds__(BB) k_scatter(BuildState st, const int32_t *__
 // The rank of an element among the same-bucket elements of its node that precede it is S(pos) - S(ptr of its node), where
 // S(pos)[k] counts the bucket-k elements at positions < pos.  S(pos) = (exclusive scan over the per-block counts that
 // k_bucket left)[block of pos] + (bucket-k elements before pos within its block): the first is a scan over n / 256 values
-// instead of n, the second four ballots per warp.  One pass notes S at every node's first position, the scatter pass
-// recomputes S for its own position and subtracts.
-__device__ __forceinline__ uint4 block_exclusive4(int bucket, uint4 (*s_warp)[BB / 32]) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned m0 = __ballot_sync(0xffffffffu, bucket == 0), m1 = __ballot_sync(0xffffffffu, bucket == 1);
-    const unsigned m2 = __ballot_sync(0xffffffffu, bucket == 2), m3 = __ballot_sync(0xffffffffu, bucket == 3);
-    if (lane == 0) (*s_warp)[warp] = make_uint4(__popc(m0), __popc(m1), __popc(m2), __popc(m3));
-    __syncthreads();
-    uint4 r = make_uint4(__popc(m0 & lt), __popc(m1 & lt), __popc(m2 & lt), __popc(m3 & lt));
-    for (unsigned w = 0; w < warp; w++) {
-        const uint4 t = (*s_warp)[w];
-        r.x += t.x, r.y += t.y, r.z += t.z, r.w += t.w;
-    }
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(BB) k_node_base4(BuildState st, const uint4 *__restrict__ block_prefix, int64_t n, uint4 *__restrict__ node_base) {
-    __shared__ uint4 s_warp[BB / 32];
-    const int64_t pos = (int64_t)blockIdx.x * BB + threadIdx.x;
-    const int slot = pos < n ? st.seg[pos] : -1;
-    const int bucket = slot >= 0 ? (int)st.bkt[pos] : -1;
-    const uint4 in_block = block_exclusive4(bucket, &s_warp);
-    if (slot >= 0 && pos == st.n_ptr[st.active[slot]]) {
-        const uint4 b = block_prefix[blockIdx.x];
-        node_base[slot] = make_uint4(b.x + in_block.x, b.y + in_block.y, b.z + in_block.z, b.w + in_block.w);
-    }
-}
-
+// instead of n, the second four ballots per warp.  k_bucket notes the in-block part of S at every node's first position,
+// the scatter pass recomputes S for its own position and subtracts.
 __global__ void __launch_bounds__(BB) k_scatter4(BuildState st, const int32_t *__restrict__ idx_in, const uint4 *__restrict__ block_prefix,
                                                 const uint4 *__restrict__ node_base, int64_t n, int32_t *__restrict__ idx_out,
                                                 int32_t *__restrict__ seg_out) {
@@ -743,10 +736,11 @@ __global__ void __launch_bounds__(BB) k_scatter4(BuildState st, const int32_t *_
         seg_out[pos] = -1;
         return;
     }
-    const uint4 b = block_prefix[blockIdx.x], base = node_base[slot];
-    const unsigned rank = pick4(make_uint4(b.x + in_block.x, b.y + in_block.y, b.z + in_block.z, b.w + in_block.w), k) - pick4(base, k);
     const int node = st.active[slot];
-    const int np = st.n_ptr[node] + st.b_start[(int64_t)slot * st.nb + k] + (int)rank;
+    const int ptr = st.n_ptr[node];
+    const uint4 b = block_prefix[blockIdx.x], first_block = block_prefix[ptr / BB], first_before = node_base[slot];
+    const unsigned rank = (pick4(b, k) + pick4(in_block, k)) - (pick4(first_block, k) + pick4(first_before, k));
+    const int np = ptr + st.b_start[(int64_t)slot * st.nb + k] + (int)rank;
     idx_out[np] = idx_in[pos];
     seg_out[np] = (np < st.split_pos[slot]) ? st.next_left[slot] : st.next_right[slot];
 }
@@ -1193,6 +1187,7 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
     st.counters = counters.p;
     st.a_minpos = a_minpos.p; st.a_maxpos = a_maxpos.p; st.b_minpos = b_minpos.p; st.b_maxpos = b_maxpos.p;
     st.block_counts = block_counts.p;
+    st.node_inblock = node_base.p;
     st.nb = nb; st.cpl = cpl;
 
     int32_t *idx_cur = idx_a.p, *idx_nxt = idx_b.p, *seg_cur = seg_a.p, *seg_nxt = seg_b.p, *act_cur = act_a.p, *act_nxt = act_b.p;
@@ -1238,8 +1233,6 @@ static int build_tree(ct_tree *tree, cudaStream_t s) {
             size_t bytes = block_scan_bytes;
             CT_CUDA(cub::DeviceScan::ExclusiveScan(block_scan_tmp.p, bytes, block_counts.p, block_prefix.p, Add4(), make_uint4(0, 0, 0, 0), n_blocks, s));
             count_launch(2);
-            k_node_base4<<<grid_for(n, BB), BB, 0, s>>>(st, block_prefix.p, n, node_base.p);
-            CT_LAUNCH_CHECK();
             k_scatter4<<<grid_for(n, BB), BB, 0, s>>>(st, idx_cur, block_prefix.p, node_base.p, n, idx_nxt, seg_nxt);
             CT_LAUNCH_CHECK();
         } else {
