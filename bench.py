@@ -864,8 +864,8 @@ def main():
                 "l2": "inputs larger than L2 (1.6 GB of points + 1.4 GB of tree per step vs 126 MB)",
                 "tree_build_ms": build_ms,
                 "tree_build_ms_first_call": build_ms_cold,
-                "queries_execution_order": "points binned by a 16-bit Z-order key (count, offsets, scatter of 32-byte records), tiles of 2048 "
-                "sorted in shared memory; results returned through per-window queues; all inside the timed step",
+                "queries_execution_order": "every point appended to the slab of its Z-order bin as a 32-byte record (one scatter pass), one "
+                "tile per bin sorted in shared memory; results returned through per-window queues; all inside the timed step",
                 "setup_s": round(setup_s, 2),
                 "tree_depth": tree.depth,
                 "tolerance": tolerance,

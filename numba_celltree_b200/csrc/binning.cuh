@@ -1,4 +1,5 @@
 // binning.cuh -- spatial binning of point queries: the execution order of ct_locate_points on large batches.
+// (The default are the SLAB bins at the end of this file; the counted bins described first are CELLTREE_ORDER=bins.)
 //
 // Queries are independent (query.py:110-117 is a prange), so which thread handles which query is an execution detail.
 // What the traversal needs from the order is (a) that the leaves a block touches are few, so that tree data comes out
@@ -67,6 +68,9 @@ __device__ __forceinline__ void load_record(const PointRecord *src, double &x, d
 }
 
 constexpr int BIN_BLOCK = 256;
+// Measurement switches (build_ext --variant TAG -DNAME=VALUE; DESIGN.md 4.2 quotes what they showed), all off by default:
+//   CT_CURSOR_STRIDE  words between the cursors of the counted bins (8 / 32: one cursor per sector / line -- no effect)
+//   CT_EXP            1: k_bin_scatter without its stores, 3: without its atomics (hashed positions; results unusable)
 #ifndef CT_CURSOR_STRIDE
 #define CT_CURSOR_STRIDE 1
 #endif

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
 // One block = one tile of TILE consecutive records (binning.cuh).  The tile is sorted by the key bits below the bin
 // (as many as the tile spans: 8 + log2(bins in the tile)), then thread t walks the tree for the sorted positions
 // t, t + 256, ...: a warp's 32 points are neighbours along the Z-order curve.  MAXV == 0: EdgeCellTree2d.
+// Measurement switch (build_ext --variant), off by default: CT_EXP2 = 1: the tile kernel without the atomics of the result
+// queues (pairs written in execution order: results unusable), 2: without the tile sort
 #ifndef CT_EXP2
 #define CT_EXP2 0
 #endif
