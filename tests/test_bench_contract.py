@@ -51,3 +51,17 @@ def test_reference_arm_is_silent_on_other_ranks():
     done = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", RANK="1", WORLD_SIZE="2")
     assert done.returncode == 0, done.stderr[-2000:]
     assert done.stdout.strip() == ""
+
+
+def test_traffic_file_is_stamped_with_a_source_hash():
+    """profiles/traffic.json carries the hash of the kernel sources its ncu capture was taken from; bench.py uses the figures
+    only when the sources that run hash the same (the GPU box has no .git to compare commits with)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    stamp = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    assert len(stamp["csrc_sha256"]) == 16 and len(bench.csrc_sha256()) == 16
+    assert stamp["traversal_dram_bytes_per_launch"] > 0 and stamp["step_dram_bytes"] >= stamp["traversal_dram_bytes_per_launch"]
+    assert any(name.startswith("k_locate_points_binned") for name in stamp["kernels"])

@@ -121,3 +121,39 @@ def test_sharded_queries_reproduce_the_unsharded_order_world2(tmp_path):
     ei, ej, ea = tree.intersect_boxes(boxes)
     got = np.load(tmp_path / "gathered.npz")
     assert np.array_equal(got["i"], ei) and np.array_equal(got["j"], ej) and np.array_equal(got["area"], ea)
+
+
+def _tensor_worker(rank, world, port, tmp):
+    import torch
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # tensor pieces (what the device-resident calls return; CPU tensors stand in for CUDA tensors under gloo): every
+        # rank's pairs go point to point into rows [offset, offset + count) of buffers preallocated on the destination
+        tree = _FakeTree()
+        boxes = np.random.default_rng(4).uniform(0, 1, (501, 4))
+        lo, hi = shard_range(len(boxes), rank, world)
+        i, j, area = tree.intersect_boxes(boxes[lo:hi])
+        offset, total, totals = exchange_totals(len(i))
+        pieces = (torch.from_numpy(i + lo), torch.from_numpy(j), torch.from_numpy(area))
+        got = gather_pairs(*pieces, offset, total, totals, dst=1)
+        if rank == 1:
+            assert all(isinstance(t, torch.Tensor) for t in got)
+            np.savez(os.path.join(tmp, "tensor_gathered.npz"), i=got[0].numpy(), j=got[1].numpy(), area=got[2].numpy())
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_pairs_moves_tensors_point_to_point_world2(tmp_path):
+    world = 2
+    port = 32500 + (os.getpid() % 2000)
+    mp.spawn(_tensor_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    tree = _FakeTree()
+    boxes = np.random.default_rng(4).uniform(0, 1, (501, 4))
+    ei, ej, ea = tree.intersect_boxes(boxes)
+    got = np.load(tmp_path / "tensor_gathered.npz")
+    assert np.array_equal(got["i"], ei) and np.array_equal(got["j"], ej) and np.array_equal(got["area"], ea)
