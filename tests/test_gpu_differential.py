@@ -127,6 +127,8 @@ def test_crowded_query_sets(pkg, delaunay_pair):
     n = 1_200_000
     crowded = np.column_stack((rng.normal(0.37, 0.002, n), rng.normal(0.61, 0.001, n)))  # nearly all in a handful of bins
     crowded[::1000] = rng.uniform(-0.1, 1.1, (len(crowded[::1000]), 2))
+    crowded[5::997] = np.nan  # NaN and far-away points share the first bin of the order
+    crowded[7::991] = [-1e300, 1e300]
     same = np.full((400_000, 2), 0.25)
     same[::3] = [0.75, 0.5]
     grid = np.stack(np.meshgrid(np.linspace(0, 1, 700), np.linspace(0, 1, 600), indexing="xy"), axis=-1).reshape(-1, 2)  # sorted rows
