@@ -1,4 +1,5 @@
-// morton.cuh -- Z-order execution order for a batch of queries (points, boxes, segments).
+// morton.cuh -- Z-order execution order for a batch of box or segment queries (and, as CELLTREE_ORDER=morton, of point
+// queries: their default order is the slab binning of binning.cuh, which needs no sort).
 //
 // Queries are independent, so the order in which threads pick them up is an execution detail: thread t handles
 // query perm[t] and writes result slot perm[t] (for variable-length results: counts[perm[t]] in the count pass,

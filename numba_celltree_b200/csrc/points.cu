@@ -1,8 +1,8 @@
-// points.cu -- ct_locate_points.  Large batches: the points are binned by a 16-bit Z-order key (binning.cuh), the
-// traversal kernel takes tiles of 2048 binned records, orders each tile in shared memory and walks the tree (entry
-// grid, treelet descent, point-in-polygon test, fused barycentric weights at the hit); results return through
-// per-window queues.  Small batches: one kernel in the caller's order.  For host buffers a chunked three-stream
-// pipeline around either.
+// points.cu -- ct_locate_points.  Large batches: every point is appended to the slab of its Z-order bin (binning.cuh), the
+// traversal kernel takes one bin per block, orders its records in shared memory and walks the tree (entry grid, treelet
+// descent, point-in-polygon test, fused barycentric weights at the hit); results return through per-window queues.
+// Small batches and trees deeper than the per-thread stack: one kernel in the caller's order.  For host buffers a chunked
+// three-stream pipeline around either.
 #include <cub/block/block_radix_sort.cuh>
 
 #include "binning.cuh"
