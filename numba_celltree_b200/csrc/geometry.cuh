@@ -570,20 +570,19 @@ CT_DEV double polygon_polygon_clip_area(const Poly<MAXA> &polygon, const Poly<MA
             P2 V{b.x - a.x, b.y - a.y};
             if (V.x == 0 && V.y == 0) continue;
             bool b_inside = sh_inside(b, r, U);
-            if (b_inside) {
-                if (!a_inside) {
-                    P2 point;
-                    if (sh_intersection(a, V, r, N, point)) push(point);
-                }
+            // The reference's four cases (sutherland_hodgman.py:118-137) with ONE site for the intersection and one for each
+            // kind of push: an edge that enters the clip half-plane and one that leaves it need the same intersection (a
+            // division: a fifth of this function's instructions), and with a site of their own each they ran it one after the
+            // other, at five active lanes.  Entering: push the intersection (if the edge is not parallel), then b.  Leaving:
+            // push the intersection -- or, if parallel, count b as inside and push it.  Both inside: push b.
+            const bool crossing = a_inside != b_inside;
+            bool have = false;
+            P2 point;
+            if (crossing) have = sh_intersection(a, V, r, N, point);
+            if (have) push(point);
+            if (b_inside || (crossing && !have)) {
+                b_inside = true;
                 push(b);
-            } else if (a_inside) {
-                P2 point;
-                if (sh_intersection(a, V, r, N, point)) {
-                    push(point);
-                } else {
-                    b_inside = true;
-                    push(b);
-                }
             }
             a = b;
             a_inside = b_inside;
