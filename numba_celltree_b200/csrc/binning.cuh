@@ -280,7 +280,8 @@ constexpr int SLAB = 2048;
 struct SlabPlan {
     uint32_t bins;  // any number, not only powers of two: bin = key24 * bins >> 24 maps the Z-order curve onto them in order
     int shift;      // a tile is sorted by (key24 - first key of its bin) >> shift ...
-    int sort_bits;  // ... which has this many bits (<= 8: two 4-bit passes of the block sort; 256 places for at most 2048 points)
+    int sort_bits;  // ... which has this many bits (<= MAX_SORT_BITS: the counters of the tile's counting sort, tile_order.cuh)
+    static constexpr int MAX_SORT_BITS = 10;
     static SlabPlan make(int64_t n) {
         SlabPlan p;
         const int64_t target = SLAB * 7 / 8;  // mean points per bin: 1792 +- 42 for uniform points, 6 deviations below the slab
@@ -291,7 +292,7 @@ struct SlabPlan {
         const uint32_t range = (uint32_t)(((uint64_t)1 << 24) / p.bins) + 2;  // keys per bin, at most
         int bits = 1;
         while (bits < 24 && (1u << bits) < range) bits++;
-        p.sort_bits = bits < 8 ? bits : 8;
+        p.sort_bits = bits < MAX_SORT_BITS ? bits : MAX_SORT_BITS;
         p.shift = bits - p.sort_bits;
         return p;
     }

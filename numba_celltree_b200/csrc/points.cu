@@ -6,6 +6,7 @@
 #include <cub/block/block_radix_sort.cuh>
 
 #include "binning.cuh"
+#include "tile_order.cuh"
 #include "traverse.cuh"
 
 namespace ct {
@@ -131,9 +132,16 @@ constexpr int TILE_THREADS = 256;
 constexpr int TILE_ITEMS = 8;
 constexpr int TILE = TILE_THREADS * TILE_ITEMS;
 
+// The order of a tile's queries: a counting sort (tile_order.cuh) when the relative keys have few bits -- every tile of the
+// slab bins, 8 to 10 bits -- and the library's block radix sort for the wide keys of the other execution orders.
 using TileSort = cub::BlockRadixSort<uint16_t, TILE_THREADS, TILE_ITEMS, uint16_t>;
+using TileCount = TileOrder<TILE_THREADS, TILE_ITEMS>;
+static_assert(SlabPlan::MAX_SORT_BITS <= ORDER_MAX_BITS, "a slab's relative keys fit the counting sort");
 struct TileShared {
-    typename TileSort::TempStorage sort;
+    union {
+        typename TileSort::TempStorage sort;
+        typename TileCount::Storage count;
+    };
     uint32_t lo, hi;
 };
 
@@ -239,34 +247,41 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         span = sh.hi - key0;
         span = span < 0xffffu ? span : 0xffffu;
     }
-    uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
-#pragma unroll
-    for (int k = 0; k < TILE_ITEMS; k++) {
-        const int j = k * TILE_THREADS + threadIdx.x;
-        uint32_t rel = 0xffffu;
-        if (j < m) {
-            rel = key24[k] - key0;
-            rel = rel < 0xffffu ? rel : 0xffffu;
-        }
-        keys[k] = (uint16_t)rel;
-        source[k] = (uint16_t)j;
-    }
 #if CT_EXP2 == 2
     const int bits = 0;
 #else
     const int bits = 32 - __clz(span | 1u);
 #endif
-    TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, bits);
-    // thread t now holds the sorted positions t, t + 256, ...: a warp's 32 points are neighbours on the Z-order curve.
-    // The point of the next position is requested while the tree is walked for the current one, and so is the
-    // slot in the result queue of the query's window (an atomic whose answer is only needed after the walk).
-    uint64_t order_lo = 0, order_hi = 0;  // source[] packed, so that the loop below can stay rolled without a local array
+    // Afterwards sh.count.order[0 .. m) lists the tile's places by key, and thread t takes the sorted positions t, t + 256,
+    // ...: a warp's 32 points are neighbours on the Z-order curve.
+    if (bits <= ORDER_MAX_BITS) {
 #pragma unroll
-    for (int k = 0; k < TILE_ITEMS; k++) {
-        if (k < 4) order_lo |= (uint64_t)source[k] << (16 * k);
-        else order_hi |= (uint64_t)source[k] << (16 * (k - 4));
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const uint32_t rel = key24[k] - key0;
+            key24[k] = rel < span ? rel : span;
+        }
+        TileCount::sort(sh.count, key24, m, bits);
+    } else {
+        uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) {
+            const int j = k * TILE_THREADS + threadIdx.x;
+            uint32_t rel = 0xffffu;
+            if (j < m) {
+                rel = key24[k] - key0;
+                rel = rel < 0xffffu ? rel : 0xffffu;
+            }
+            keys[k] = (uint16_t)rel;
+            source[k] = (uint16_t)j;
+        }
+        TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, bits);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TILE_ITEMS; k++) sh.count.order[k * TILE_THREADS + threadIdx.x] = source[k];  // places >= m sort last
+        __syncthreads();
     }
-    static_assert(TILE_ITEMS == 8, "source[] is packed into two 64-bit words");
+    // The point of the next position is requested while the tree is walked for the current one, and so is the slot in the
+    // result queue of the query's window (an atomic whose answer is only needed after the walk).
     double x = 0.0, y = 0.0;
     uint32_t index = 0;
     auto fetch = [&](int j) {
@@ -279,18 +294,15 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
             load_record(tile + j, x, y, index, key);
         }
     };
-    int j = (int)(order_lo & 0xffffu);
-    if (j < m) fetch(j);
+    int position = threadIdx.x;
+    if (position < m) fetch(sh.count.order[position]);
 #pragma unroll 1
     for (int k = 0; k < TILE_ITEMS; k++) {
-        const bool valid = j < m;
+        if (position >= m) break;  // positions only grow
         const P2 p{x, y};
         const uint32_t my_index = index;
-        if (k + 1 < TILE_ITEMS) {
-            j = (int)(((k + 1 < 4 ? order_lo : order_hi) >> (16 * ((k + 1) & 3))) & 0xffffu);
-            if (j < m) fetch(j);
-        }
-        if (!valid) continue;
+        position += TILE_THREADS;
+        if (position < m) fetch(sh.count.order[position]);
         uint32_t slot = 0;
 #if CT_EXP2 != 1
         if (pairs) slot = atomicAdd(window_cursor + (my_index >> WINDOW_BITS), 1u);
