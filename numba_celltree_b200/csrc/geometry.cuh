@@ -106,14 +106,14 @@ template <int MAXV>
 CT_DEV void load_tree_polygon(const TreeView &t, int64_t elem, Poly<MAXV> &poly) {
     if constexpr (MAXV <= 4) {
         if (!t.length_from_rows) {
-            const int M = t.M;
+            constexpr int M = MAXV;  // every launcher picks the 3- and 4-vertex kernels for exactly that row width
             const double2 *c = t.elem_xy + elem * (int64_t)M;
             double2 v[MAXV];
 #pragma unroll
-            for (int k = 0; k < MAXV; k++) v[k] = (k < M) ? __ldg(c + k) : make_double2(0.0, 0.0);
-            int n = M < MAXV ? M : MAXV;
+            for (int k = 0; k < MAXV; k++) v[k] = __ldg(c + k);
+            int n = MAXV;
             if constexpr (MAXV == 4) {
-                if (M == 4 && (unsigned long long)__double_as_longlong(v[3].x) == PAD_VERTEX_BITS) n = 3;
+                if ((unsigned long long)__double_as_longlong(v[3].x) == PAD_VERTEX_BITS) n = 3;
             }
             poly.n = n;
 #pragma unroll
@@ -235,6 +235,70 @@ CT_DEV bool point_in_polygon_or_on_edge(P2 p, const Poly<MAXV> &poly, double tol
         return c;
     }
 }
+
+// True only where point_in_polygon_or_on_edge above is CERTAIN to answer false: the point lies beyond the polygon's bounding
+// box by more than a margin.  The reference has no such test (query.py:77-85 runs the full test on every cell of a leaf);
+// it is here so that the lanes of a warp first pick their candidate cell -- neighbouring points sit in different cells of the
+// same leaf -- and then run the expensive test together, once, instead of one after the other on every cell.
+//
+// Why the answer is certain.  Let the point be beyond every vertex in one coordinate, say p.x - v.x > m for all vertices
+// (the other three sides alike), m = 8 |tolerance| + 1e-12 * (sum of |v.x|) + 2e-150.
+//  * Acceptance on an edge needs in_bounds: an edge bounded in x fails it exactly (comparisons only).  For an edge bounded
+//    in y (|dy| > |dx|) with p.y inside its range, U.y and V.y have opposite signs and U.x, V.x the same sign, so the two
+//    products of A = U.x V.y - U.y V.x have the same sign -- no cancellation: |A| >= m (|U.y| + |V.y|) = m |dy| >= m |W| / sqrt 2,
+//    A^2 >= 32 tolerance^2 |W|^2, while the right-hand side tolerance * |W|^2 * tolerance is at most 8 times its exact
+//    value even where |W|^2 or the products fall into the denormal range (each of three roundings at most doubles a denormal):
+//    not accepted.
+//  * The crossing test: beyond in y there is no straddling edge (exact comparisons).  Beyond in x, every straddling edge
+//    computes its intersection abscissa (dx * (p.y - v0.y)) / dy + v0.x within 16 ulp-sized errors of the edge's x-range --
+//    1e-12 * sum |v.x| is 250 times that -- unless the product underflows, where the error is at most |dx| (the quotient
+//    lies between 0 and 2 dx): |dx| < 1e-150 is covered by the 2e-150 of the margin, and |dx| >= 1e-150 needs
+//    0 < |p.y - v0.y| < 2.2e-158 to underflow, which outside_x_sides_allowed() below excludes once per point.  So all
+//    straddling edges answer alike, and their number is even (the booleans v.y > p.y around a closed polygon change an even
+//    number of times): c stays false.  Huge coordinates, whose products could overflow, switch the x sides off.
+// Comparisons with NaN are false, so a NaN anywhere (coordinates, point, tolerance) never rejects.
+template <int MAXV>
+CT_DEV bool point_surely_outside(P2 p, const Poly<MAXV> &poly, double margin, bool x_sides_allowed) {
+    double sx = 0.0, sy = 0.0;
+    bool xhi = true, xlo = true, yhi = true, ylo = true;
+    auto vertex = [&](double vx, double vy) {
+        sx += fabs(vx);
+        sy += fabs(vy);
+    };
+    auto side = [&](double vx, double vy, double mx, double my) {
+        const double dx = p.x - vx, dy = p.y - vy;
+        xhi = xhi && dx > mx;
+        xlo = xlo && dx < -mx;
+        yhi = yhi && dy > my;
+        ylo = ylo && dy < -my;
+    };
+    if constexpr (MAXV == 3 || MAXV == 4) {
+        // a triangle in a four-vertex row counts its first vertex twice (the fourth slot holds the padding marker)
+        const bool four = MAXV == 4 && poly.n == 4;
+        const double x3 = four ? poly.x[MAXV - 1] : poly.x[0], y3 = four ? poly.y[MAXV - 1] : poly.y[0];
+#pragma unroll
+        for (int k = 0; k < 3; k++) vertex(poly.x[k], poly.y[k]);
+        vertex(x3, y3);
+        const double mx = fma(sx, 1e-12, margin), my = fma(sy, 1e-12, margin);
+#pragma unroll
+        for (int k = 0; k < 3; k++) side(poly.x[k], poly.y[k], mx, my);
+        side(x3, y3, mx, my);
+    } else {
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+            if (k < poly.n) vertex(poly.x[k], poly.y[k]);
+        const double mx = fma(sx, 1e-12, margin), my = fma(sy, 1e-12, margin);
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+            if (k < poly.n) side(poly.x[k], poly.y[k], mx, my);
+    }
+    return yhi || ylo || ((xhi || xlo) && x_sides_allowed && (sx + sy) < 1e100);
+}
+// Whether the x sides of point_surely_outside may be used for this point: a point whose |y| is at least 1e-140 differs from
+// any other y coordinate by zero or by more than 5e-157 (the difference of two doubles is a multiple of the smaller one's
+// unit in the last place), so with |dx| >= 1e-150 the product dx * (p.y - v0.y) of the crossing test cannot underflow.
+CT_DEV bool outside_x_sides_allowed(P2 p) { return fabs(p.y) >= 1e-140; }
+CT_DEV double outside_margin(double tolerance) { return fma(8.0, fabs(tolerance), 2e-150); }
 
 CT_DEV bool point_on_edge(P2 p, P2 v0, P2 v1, double tolerance) {  // geometry_utils.py:226-238
     if (v1.x == v0.x && v1.y == v0.y) return false;

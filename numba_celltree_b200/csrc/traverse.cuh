@@ -128,8 +128,11 @@ CT_DEV uint32_t entry_handle(const EntryGrid &g, P2 p) {
     if (g.handle == nullptr) return ROOT_HANDLE;
     const int shift = 16 - g.bits;
     const uint32_t cx = grid_coord(p.x, g.xmin, g.sx) >> shift, cy = grid_coord(p.y, g.ymin, g.sy) >> shift;
-    const bool inside = p.x > __ldg(g.lo + cx) && p.y > __ldg(g.lo + (1 << g.bits) + cy);  // false for NaN
-    return inside ? __ldg(g.handle + ((cy << g.bits) | cx)) : ROOT_HANDLE;
+    // the three reads are independent (grid_coord() stays inside the table for any input), so they travel together
+    const double lo_x = __ldg(g.lo + cx), lo_y = __ldg(g.lo + (1 << g.bits) + cy);
+    const uint32_t handle = __ldg(g.handle + ((cy << g.bits) | cx));
+    const bool inside = p.x > lo_x && p.y > lo_y;  // false for NaN
+    return inside ? handle : ROOT_HANDLE;
 }
 
 CT_DEV int4 cursor_leaf(const Cursor &c) {  // {ptr, size, id0, id1}
@@ -182,6 +185,8 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe 
     Cursor c;
     Probe none;
     Probe &pr = probe ? *probe : none;
+    const double margin = outside_margin(tolerance);
+    const bool x_sides = outside_x_sides_allowed(p);
     // a move within a treelet reads the node's slot; entering a treelet reads its header as well
     auto descend = [&](uint32_t child) {
         pr.slot();
@@ -221,17 +226,28 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe 
                 enter(stack.pop(t));
             }
         }
+        // The cells of the leaf in their order (query.py:77-85).  Every lane first moves on to its next cell that the point
+        // is not surely outside of (geometry.cuh: point_surely_outside -- a few comparisons on the vertices just read), then
+        // the lanes of the warp run the point-in-polygon test together: the points of a warp are neighbours, so they share
+        // the leaf but not the cell, and testing cell after cell would run the whole test once per cell with part of the lanes.
         const int4 leaf = cursor_leaf(c);
-        int found = -1;
-        if (for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
-                Poly<MAXV> poly;
+        for (int k = 0; k < leaf.y;) {
+            Poly<MAXV> poly;
+            int candidate = -1;
+            while (k < leaf.y) {
+                const int bbox_index = leaf_element(leaf, t.bb_indices, k++);
                 pr.cell();
                 load_tree_polygon<MAXV>(t, bbox_index, poly);
-                if (!point_in_polygon_or_on_edge(p, poly, tolerance)) return false;
-                found = bbox_index;
-                return true;
-            }))
-            return found;
+                if (!point_surely_outside(p, poly, margin, x_sides)) {
+                    candidate = bbox_index;
+                    break;
+                }
+            }
+            // (the empty statement keeps the compiler from sending every exit of the loop above straight to its own copy of
+            // the test below: the lanes must meet again here, after the loop)
+            asm volatile("" : "+r"(candidate));
+            if (candidate >= 0 && point_in_polygon_or_on_edge(p, poly, tolerance)) return candidate;
+        }
         if (stack.empty()) return -1;
         enter(stack.pop(t));
     }

@@ -533,3 +533,55 @@ def test_unbucketable_centroid_raises_like_the_reference(pkg):
         oracle.CellTree2d(vertices, faces, -1, cells_per_leaf=1)
     with pytest.raises(IndexError):
         pkg.CellTree2d(vertices, faces, -1, cells_per_leaf=1)
+
+
+def mixed_mesh(n_points, seed):
+    """Triangles, quads (pairs of Delaunay triangles merged) and padded rows in one face array of width 4."""
+    vertices, tri = delaunay_mesh(n_points, seed)
+    faces = np.full((len(tri), 4), -1, dtype=tri.dtype)
+    faces[:, :3] = tri
+    return vertices, faces
+
+
+def hexagon_mesh(nx, ny):
+    """Rows of regular hexagons (six vertices a face, the generic polygon path), every other row shifted."""
+    angles = np.pi / 3 * np.arange(6)
+    ring = np.column_stack((np.cos(angles), np.sin(angles)))
+    centres = np.array([(1.5 * i, np.sqrt(3) * (j + 0.5 * (i % 2))) for j in range(ny) for i in range(nx)])
+    corners = (centres[:, None, :] + ring[None, :, :]).reshape(-1, 2)
+    unique, inverse = np.unique(np.round(corners, 9), axis=0, return_inverse=True)
+    return unique, inverse.reshape(-1, 6).astype(np.int64)
+
+
+@pytest.mark.filterwarnings("ignore:overflow encountered", "ignore:invalid value encountered")
+def test_the_bounding_filter_never_changes_an_answer(pkg):
+    """The traversal skips a cell's point-in-polygon test when the point is surely outside the cell's bounds
+    (geometry.cuh: point_surely_outside); the reference tests every cell of a leaf.  Tolerances from zero to infinity,
+    negative and NaN, points on and a few ulps around the cells' bounding lines and on the extensions of their edges,
+    coordinates shifted to 1e7 (tolerance below one ulp), scaled to 1e-160 / 1e-300 (products underflow) and to 1e150 /
+    1e300 (products overflow)."""
+    rng = np.random.default_rng(77)
+    meshes = [delaunay_mesh(3_000, seed=5), mixed_mesh(2_000, seed=6), quad_mesh(40, 30), hexagon_mesh(12, 10)]
+    for vertices, faces in meshes:
+        lo, hi = vertices.min(0), vertices.max(0)
+        span = hi - lo
+        n_vert = (faces >= 0).sum(1)
+        first = vertices[faces[:, 0]]
+        second = vertices[faces[:, 1]]
+        t = rng.uniform(-1.5, 2.5, (len(faces), 1))
+        on_lines = first + t * (second - first)  # on the (extended) line through an edge of every cell
+        pick = vertices[rng.integers(0, len(vertices), 3_000)]
+        cross = np.column_stack((pick[:, 0], pick[::-1, 1]))  # on the bounding lines of two different cells
+        base = np.concatenate([rng.uniform(lo - 0.1 * span, hi + 0.1 * span, (10_000, 2)), on_lines, pick, cross])
+        points = np.concatenate([base, np.nextafter(base, -np.inf), np.nextafter(base, np.inf), base + 1e-9, base - 3e-7])
+        for shift, scale in ((0.0, 1.0), (1e7, 1.0), (0.0, 1e-160), (0.0, 1e-300), (0.0, 1e150), (0.0, 1e300), (-3e5, 37.0)):
+            v = (vertices + shift) * scale
+            q = (points + shift) * scale
+            every = (None, 0.0, 1e-9 * scale, 0.02 * span[0] * scale, 3.0 * span[0] * scale, -1e-3 * scale, np.inf, np.nan)
+            for cells_per_leaf, tolerances in ((2, every), (5, every[::3])):
+                tree = pkg.CellTree2d(v, faces, -1, cells_per_leaf=cells_per_leaf)
+                ref = oracle.CellTree2d(v, faces, -1, cells_per_leaf=cells_per_leaf)
+                for tolerance in tolerances:
+                    got = tree.locate_points(q, tolerance)
+                    want = ref.locate_points(q, tolerance)
+                    assert np.array_equal(got, want), (shift, scale, tolerance, int(n_vert.max()))
