@@ -583,15 +583,18 @@ def multi_gpu_section(torch, dist, ctd, tree, device, rank, world, n_points, ste
     def strong_step():
         found = tree.locate_points(mine)
         if assembled is not None:
-            dist.all_gather_into_tensor(assembled, found)
+            ctd.assemble_indices(found, out=assembled)
         return found
 
     ms, found = synced_ms(strong_step, steps)
     checksum = int(assembled.sum().item()) if assembled is not None else None
+    sharded_ms, _ = synced_ms(lambda: tree.locate_points(mine), steps)  # the same step without the assembly
     strong = {
         "metric": METRIC, "scaling": "strong", "total_queries": n_points, "per_gpu_queries": hi - lo, "ms_per_step": ms,
         "value": n_points / (ms * 1e-3), "unit": UNIT,
-        "assembled": "all_gather_into_tensor of the int64 results on every GPU (NCCL), inside the timed step" if equal_shards else "left sharded",
+        "assembled": "distributed.assemble_indices: results narrowed to int32, one all_gather_into_tensor (NCCL), widened to int64 on every GPU, inside the timed step" if equal_shards else "left sharded",
+        "ms_per_step_left_sharded": sharded_ms,
+        "assembly_bytes_received_per_gpu": (n_points - (hi - lo)) * 4 if equal_shards else 0,
         "result_checksum": checksum,
     }  # fmt: skip
     del mine, assembled, found

@@ -7,7 +7,7 @@ no collective, and variable-length results need exactly one all-gather of the pe
 local offsets into global offsets.  Concatenating the per-rank results in rank order reproduces the
 single-GPU (= the reference's) output order.
 
-The host-side logic (shard_range, exchange_totals, the *_sharded calls, gather_pairs) is backend-agnostic and is
+The host-side logic (shard_range, exchange_totals, the *_sharded calls, assemble_indices, gather_pairs) is backend-agnostic and is
 exercised with gloo on CPU in tests/test_distributed.py.
 """
 
@@ -81,6 +81,34 @@ def locate_points_sharded(tree, points, tolerance=None, weights: bool = False):
     mine = _rows(points, lo, hi)
     result = tree.compute_barycentric_weights(mine, tolerance) if weights else tree.locate_points(mine, tolerance)
     return lo, hi, result
+
+
+def assemble_indices(local, out=None, narrow: bool = True):
+    """
+    Every rank's share of a fixed-size index result (``locate_points_sharded``: cell indices, -1 = outside), put together
+    on EVERY rank in query order: one all-gather of equal shards.  Cell indices fit 32 bits (the tree holds fewer than
+    2**31 cells, `ct_tree_info.n_elem`), so with `narrow` they travel as int32 -- half the bytes over NVLink -- and are
+    widened to the API's int64 on arrival.  `local` is a torch tensor (CUDA under NCCL) or a NumPy array; all shards must
+    have the same length (``n % world == 0``; otherwise keep the result sharded or use `gather_pairs`-style transfers).
+    `out`: optional preallocated int64 tensor of world * len(local) entries.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    as_numpy = isinstance(local, np.ndarray)
+    piece = torch.from_numpy(np.ascontiguousarray(local)) if as_numpy else local.contiguous()
+    if as_numpy and dist.get_backend() == "nccl":
+        piece = piece.to(_collective_device())
+    if narrow:
+        piece = piece.to(torch.int32)
+    gathered = torch.empty(world * piece.shape[0], dtype=piece.dtype, device=piece.device)
+    dist.all_gather_into_tensor(gathered, piece)
+    if out is None:
+        out = gathered.to(torch.int64)
+    else:
+        out.copy_(gathered)
+    return out.cpu().numpy() if as_numpy else out
 
 
 def query_pairs_sharded(tree, method: str, queries, *args, device=None):

@@ -8,6 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from numba_celltree_b200.distributed import (
+    assemble_indices,
     exchange_totals,
     gather_pairs,
     globalize_pairs,
@@ -144,6 +145,18 @@ def _tensor_worker(rank, world, port, tmp):
             np.savez(os.path.join(tmp, "tensor_gathered.npz"), i=got[0].numpy(), j=got[1].numpy(), area=got[2].numpy())
         else:
             assert got is None
+        # fixed-size results of equal shards, assembled on every rank (narrowed to int32 on the way), tensors and NumPy
+        points = np.random.default_rng(13).uniform(0, 1, (1000, 2))
+        points[::17] = 2.0
+        lo, hi, found = locate_points_sharded(tree, points)
+        found = np.where(points[lo:hi, 0] > 1.0, -1, found)
+        for narrow in (True, False):
+            whole = assemble_indices(torch.from_numpy(found), narrow=narrow)
+            assert whole.dtype == torch.int64
+            np.save(os.path.join(tmp, f"assembled{rank}_{int(narrow)}.npy"), whole.numpy())
+        into = torch.empty(len(points), dtype=torch.int64)
+        assert assemble_indices(torch.from_numpy(found), out=into) is into
+        assert np.array_equal(into.numpy(), assemble_indices(found))
     finally:
         dist.destroy_process_group()
 
@@ -157,3 +170,9 @@ def test_gather_pairs_moves_tensors_point_to_point_world2(tmp_path):
     ei, ej, ea = tree.intersect_boxes(boxes)
     got = np.load(tmp_path / "tensor_gathered.npz")
     assert np.array_equal(got["i"], ei) and np.array_equal(got["j"], ej) and np.array_equal(got["area"], ea)
+    points = np.random.default_rng(13).uniform(0, 1, (1000, 2))
+    points[::17] = 2.0
+    expected = np.where(points[:, 0] > 1.0, -1, tree.locate_points(points))
+    for rank in range(world):
+        for narrow in (0, 1):
+            assert np.array_equal(np.load(tmp_path / f"assembled{rank}_{narrow}.npy"), expected)
