@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         }
         TileCount::sort(sh.count, key24, m, bits);
     } else {
+        // wide keys (a sparse tile of the counted bins or of the sorted permutation): valid keys saturate at 0xfffe and the
+        // empty places of the last, partial tile carry 0xffff -- compared over all 16 bits there, so that they sort strictly
+        // last and the first m sorted positions are exactly the tile's points
         uint16_t keys[TILE_ITEMS], source[TILE_ITEMS];
 #pragma unroll
         for (int k = 0; k < TILE_ITEMS; k++) {
@@ -269,12 +272,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
             uint32_t rel = 0xffffu;
             if (j < m) {
                 rel = key24[k] - key0;
-                rel = rel < 0xffffu ? rel : 0xffffu;
+                rel = rel < 0xfffeu ? rel : 0xfffeu;
             }
             keys[k] = (uint16_t)rel;
             source[k] = (uint16_t)j;
         }
-        TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, bits);
+        TileSort(sh.sort).SortBlockedToStriped(keys, source, 0, m < TILE ? 16 : bits);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < TILE_ITEMS; k++) sh.count.order[k * TILE_THREADS + threadIdx.x] = source[k];  // places >= m sort last

@@ -585,3 +585,38 @@ def test_the_bounding_filter_never_changes_an_answer(pkg):
                     got = tree.locate_points(q, tolerance)
                     want = ref.locate_points(q, tolerance)
                     assert np.array_equal(got, want), (shift, scale, tolerance, int(n_vert.max()))
+
+
+ORDER_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import oracle
+from numba_celltree_b200 import CellTree2d, _lib
+from numba_celltree_b200.synthetic import delaunay_mesh, quad_mesh
+_lib.load().ct_set_sort_bits(16)  # the binned path also for these small batches
+rng = np.random.default_rng(3)
+for vertices, faces in (delaunay_mesh(20_000, seed=9), quad_mesh(300, 200)):
+    tree, ref = CellTree2d(vertices, faces, -1), oracle.CellTree2d(vertices, faces, -1)
+    uniform = rng.uniform(-0.05, 1.05, (30_000, 2))
+    crowded = np.concatenate([uniform[:7_000], rng.normal(0.4, 0.0005, (9_000, 2)), np.full((3_000, 2), 0.7)])
+    sparse = np.concatenate([rng.uniform(0, 1, (300, 2)), [[np.nan, 0.5], [1e300, -1e300]]])
+    for points in (uniform, crowded, sparse, uniform[:2048], uniform[:2049], uniform[:1]):
+        got, want = tree.compute_barycentric_weights(points), ref.compute_barycentric_weights(points)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), len(points)
+print("same answers")
+"""
+
+
+@pytest.mark.parametrize("order", ["slabs", "bins", "sort", "morton"])
+def test_every_execution_order_gives_the_oracles_answers(order):
+    """CELLTREE_ORDER is read once per process, so every order runs in a process of its own: full, partial and
+    single-point tiles, crowded and sparse batches through the binned kernels."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CELLTREE_ORDER=order)
+    done = subprocess.run([sys.executable, "-c", ORDER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
+    assert done.returncode == 0 and "same answers" in done.stdout, done.stdout[-2000:] + done.stderr[-4000:]
