@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(BLOCK) k_locate_points_on_edge(TreeView t, con
 #ifndef CT_WEIGHTS_MINB
 #define CT_WEIGHTS_MINB 4  // the same with fused barycentric weights (C2, 100 M points: 2 -> 11.9 ms, 3 -> 11.1, 4 -> 10.6)
 #endif
+#ifndef CT_PREFETCH_RECORD
+#define CT_PREFETCH_RECORD 0  // 1: the next record is asked into L1 by a prefetch instead of being loaded one iteration ahead
+                              // (five live values across the walk): fewer spills in the FILTER kernels, but 3.44 against 3.22 ms
+#endif
 #ifndef CT_TILE_MINB
 #define CT_TILE_MINB 4  // blocks per SM of the 3- and 4-vertex kernels (64 registers)
 #endif
@@ -154,6 +158,7 @@ struct TileInput {
     BinGrid grid;
     const uint32_t *slab_fill;   // slab bins (binning.cuh): tile b is bin b, records [b * SLAB, b * SLAB + min(fill[b], SLAB)) ...
     SlabPlan plan;               // ... sorted by the key relative to the bin's first key
+    bool crowded_leaves;         // host side only: the tree's leaves hold more than two cells (picks the kernel variant)
 };
 
 CT_DEV double2 load_point_once(const double2 *p) {
@@ -162,7 +167,7 @@ CT_DEV double2 load_point_once(const double2 *p) {
     return v;
 }
 
-template <int MAXV, bool WEIGHTS, int MINB, bool GATHER>
+template <int MAXV, bool WEIGHTS, int MINB, bool GATHER, bool FILTER>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
     k_locate_points_binned(TreeView t, TileInput in, int64_t n, double tolerance, uint2 *__restrict__ pairs,
                            uint32_t *__restrict__ window_cursor, int64_t *__restrict__ out, double *__restrict__ weights) {
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         for (int k = 0; k < TILE_ITEMS; k++) sh.count.order[k * TILE_THREADS + threadIdx.x] = source[k];  // places >= m sort last
         __syncthreads();
     }
-    // The point of the next position is requested while the tree is walked for the current one, and so is the slot in the
+    // The record of the next position is requested while the tree is walked for the current one, and so is the slot in the
     // result queue of the query's window (an atomic whose answer is only needed after the walk).
     double x = 0.0, y = 0.0;
     uint32_t index = 0;
@@ -297,22 +302,40 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
             load_record(tile + j, x, y, index, key);
         }
     };
-    int position = threadIdx.x;
-    if (position < m) fetch(sh.count.order[position]);
+    auto ask = [&](int position) {
+        if constexpr (!GATHER) {
+            if (position < m) asm volatile("prefetch.global.L1 [%0];" ::"l"(tile + sh.count.order[position]));
+        }
+    };
+#if CT_PREFETCH_RECORD
+    ask(threadIdx.x);
+#else
+    if ((int)threadIdx.x < m) fetch(sh.count.order[threadIdx.x]);
+#endif
 #pragma unroll 1
-    for (int k = 0; k < TILE_ITEMS; k++) {
-        if (position >= m) break;  // positions only grow
+    for (int position = threadIdx.x; position < m;) {
+#if CT_EXP2 == 1
+        const int k = position / TILE_THREADS;
+#endif
+#if CT_PREFETCH_RECORD
+        fetch(sh.count.order[position]);
+        position += TILE_THREADS;
+        ask(position);
+        const P2 p{x, y};
+        const uint32_t my_index = index;
+#else
         const P2 p{x, y};
         const uint32_t my_index = index;
         position += TILE_THREADS;
         if (position < m) fetch(sh.count.order[position]);
+#endif
         uint32_t slot = 0;
 #if CT_EXP2 != 1
         if (pairs) slot = atomicAdd(window_cursor + (my_index >> WINDOW_BITS), 1u);
 #endif
         int found;
         if constexpr (MAXV == 0) found = locate_point_on_edge(t, p, tolerance);
-        else found = locate_point<MAXV>(t, p, tolerance);
+        else found = locate_point<MAXV, NoProbe, false, FILTER>(t, p, tolerance);
         // (index, result) -> the queue of the index's window; small batches: straight to out (L2 merges the stores)
 #if CT_EXP2 == 1
         if (pairs) pairs[base + k * TILE_THREADS + threadIdx.x] = make_uint2(my_index, (uint32_t)found);
@@ -374,12 +397,17 @@ static int launch_locate_points_binned(const TreeView &v, const TileInput &in, i
         else gathered<<<grid, TILE_THREADS, 0, s>>>(v, in, n, tol, pairs, window_cursor, out, weights);
         return CT_OK;
     };
+    // FILTER (traverse.cuh: the bounding test before the point-in-polygon test): always for the fused weights (C2: 9.85 ->
+    // 9.54 ms) and the generic polygons; for the plain 3- and 4-vertex kernels only when a leaf holds more than two cells --
+    // with the default two it saves 11 % of the instructions and no time, and costs the kernel its spill-free 64 registers
     if (weights) {
-        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), false>, k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), true>));
-    } else if (MAXV <= 4)
-        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB, false>, k_locate_points_binned<MAXV, false, CT_TILE_MINB, true>));
+        if constexpr (MAXV > 0) CT_CHECK(launch(k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), false, true>, k_locate_points_binned<MAXV, true, (MAXV <= 4 ? CT_WEIGHTS_MINB : 2), true, true>));
+    } else if (MAXV <= 4 && in.crowded_leaves)
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB, false, true>, k_locate_points_binned<MAXV, false, CT_TILE_MINB, true, true>));
+    else if (MAXV <= 4)
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, CT_TILE_MINB, false, false>, k_locate_points_binned<MAXV, false, CT_TILE_MINB, true, false>));
     else
-        CT_CHECK(launch(k_locate_points_binned<MAXV, false, 2, false>, k_locate_points_binned<MAXV, false, 2, true>));
+        CT_CHECK(launch(k_locate_points_binned<MAXV, false, 2, false, true>, k_locate_points_binned<MAXV, false, 2, true, true>));
     CT_LAUNCH_CHECK();
     return CT_OK;
 }
@@ -482,7 +510,7 @@ static int locate_points_device(const ct_tree *tree, const double2 *pts, int64_t
     PointBins bins;
     BinSort sorted;
     PointSlabs slabs;
-    TileInput in{nullptr, nullptr, pts, BinGrid{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy}, nullptr, SlabPlan{}};
+    TileInput in{nullptr, nullptr, pts, BinGrid{tree->bbox[0], tree->bbox[2], tree->grid_sx, tree->grid_sy}, nullptr, SlabPlan{}, tree->cells_per_leaf > 2};
     if (order_mode == 3 && n > ((int64_t)400 << 20)) order_mode = 0;  // the slabs of that many points: too much memory
     if (order_mode == 3) {
         CT_CHECK(slabs.build(tree, pts, n, s));

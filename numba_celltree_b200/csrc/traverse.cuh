@@ -178,7 +178,7 @@ struct CountingProbe {
     CT_DEV void entry(bool from_grid) { entries += from_grid ? 1u : 0u; }
 };
 
-template <int MAXV, typename Probe = NoProbe, bool DEEP = false>
+template <int MAXV, typename Probe = NoProbe, bool DEEP = false, bool FILTER = true>
 CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe = nullptr) {
     CT_STACK(stack, DEEP);
     const char *base = reinterpret_cast<const char *>(t.treelets);
@@ -226,27 +226,43 @@ CT_DEV int locate_point(const TreeView &t, P2 p, double tolerance, Probe *probe 
                 enter(stack.pop(t));
             }
         }
-        // The cells of the leaf in their order (query.py:77-85).  Every lane first moves on to its next cell that the point
-        // is not surely outside of (geometry.cuh: point_surely_outside -- a few comparisons on the vertices just read), then
-        // the lanes of the warp run the point-in-polygon test together: the points of a warp are neighbours, so they share
-        // the leaf but not the cell, and testing cell after cell would run the whole test once per cell with part of the lanes.
         const int4 leaf = cursor_leaf(c);
-        for (int k = 0; k < leaf.y;) {
-            Poly<MAXV> poly;
-            int candidate = -1;
-            while (k < leaf.y) {
-                const int bbox_index = leaf_element(leaf, t.bb_indices, k++);
-                pr.cell();
-                load_tree_polygon<MAXV>(t, bbox_index, poly);
-                if (!point_surely_outside(p, poly, margin, x_sides)) {
-                    candidate = bbox_index;
-                    break;
+        if constexpr (FILTER) {
+            // The cells of the leaf in their order (query.py:77-85).  Every lane first moves on to its next cell that the
+            // point is not surely outside of (geometry.cuh: point_surely_outside -- comparisons on the vertices just read),
+            // then the lanes of the warp run the point-in-polygon test together: the points of a warp are neighbours, so
+            // they share the leaf but not the cell, and testing cell after cell runs the whole test once per cell with part
+            // of the lanes.
+            for (int k = 0; k < leaf.y;) {
+                Poly<MAXV> poly;
+                int candidate = -1;
+                while (k < leaf.y) {
+                    const int bbox_index = leaf_element(leaf, t.bb_indices, k++);
+                    pr.cell();
+                    load_tree_polygon<MAXV>(t, bbox_index, poly);
+                    if (!point_surely_outside(p, poly, margin, x_sides)) {
+                        candidate = bbox_index;
+                        break;
+                    }
                 }
+                // (the empty statement keeps the compiler from sending every exit of the loop above straight to its own copy
+                // of the test below: the lanes must meet again here, after the loop)
+                asm volatile("" : "+r"(candidate));
+                if (candidate >= 0 && point_in_polygon_or_on_edge(p, poly, tolerance)) return candidate;
             }
-            // (the empty statement keeps the compiler from sending every exit of the loop above straight to its own copy of
-            // the test below: the lanes must meet again here, after the loop)
-            asm volatile("" : "+r"(candidate));
-            if (candidate >= 0 && point_in_polygon_or_on_edge(p, poly, tolerance)) return candidate;
+        } else {
+            // the reference's loop as it stands: with two cells per leaf (the default) the bounding test above saves
+            // instructions but not time, and its live values cost the 3- and 4-vertex kernels their spill-free 64 registers
+            int found = -1;
+            if (for_each_leaf_element(leaf, t.bb_indices, [&](int bbox_index) {
+                    Poly<MAXV> poly;
+                    pr.cell();
+                    load_tree_polygon<MAXV>(t, bbox_index, poly);
+                    if (!point_in_polygon_or_on_edge(p, poly, tolerance)) return false;
+                    found = bbox_index;
+                    return true;
+                }))
+                return found;
         }
         if (stack.empty()) return -1;
         enter(stack.pop(t));

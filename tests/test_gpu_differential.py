@@ -604,6 +604,12 @@ for vertices, faces in (delaunay_mesh(20_000, seed=9), quad_mesh(300, 200)):
     for points in (uniform, crowded, sparse, uniform[:2048], uniform[:2049], uniform[:1]):
         got, want = tree.compute_barycentric_weights(points), ref.compute_barycentric_weights(points)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), len(points)
+        assert np.array_equal(tree.locate_points(points), want[0])
+    # leaves of more than two cells: the kernels that pick the candidate cell by its bounds first
+    tree, ref = CellTree2d(vertices, faces, -1, cells_per_leaf=6), oracle.CellTree2d(vertices, faces, -1, cells_per_leaf=6)
+    for points in (uniform, crowded):
+        for tolerance in (None, 0.0, 0.01):
+            assert np.array_equal(tree.locate_points(points, tolerance), ref.locate_points(points, tolerance))
 print("same answers")
 """
 
