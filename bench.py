@@ -527,8 +527,9 @@ def secondary_metrics(torch, tree_c2, dev_points, n_points, peak):
     return out
 
 
-def c1_reference_line():
-    """C1 of BASELINE.json: the reference itself on its own CPU-runnable case (generate_disk(25, 20) + 1 M points)."""
+def c1_reference_line(torch=None):
+    """C1 of BASELINE.json: the reference itself on its own CPU-runnable case (generate_disk(25, 20) + 1 M points), and this
+    library on the same case beside it (NumPy to NumPy, and device-resident), answers compared."""
     sys.path.insert(0, str(ROOT / "baseline"))
     try:
         import reference as ref_arm
@@ -543,10 +544,24 @@ def c1_reference_line():
     pts = c1_points()
     tree.locate_points(pts[:1000])
     _, best, result = ref_arm.time_calls(lambda: tree.locate_points(pts), 3)
-    return {
+    line = {
         "config": "C1", "call": "numba_celltree.CellTree2d.locate_points (reference, CPU)", "units": len(pts), "unit": "queries",
         "queries_per_s": len(pts) / best, "cores": info["numba_threads"], "cells": len(f), "found_fraction": float((result >= 0).mean()),
     }  # fmt: skip
+    if torch is not None:
+        import numpy as np
+
+        from numba_celltree_b200 import CellTree2d
+
+        ours = CellTree2d(v, f, -1)
+        e2e, found = host_ms(torch, lambda: ours.locate_points(pts), reps=5)
+        dev_pts = torch.from_numpy(pts).cuda()
+        dev, _ = device_ms(torch, lambda: ours.locate_points(dev_pts), reps=5)
+        line["this_library"] = {
+            "e2e_ms": e2e, "e2e_queries_per_s": len(pts) / (e2e * 1e-3), "device_ms": dev, "device_queries_per_s": len(pts) / (dev * 1e-3),
+            "same_answers_as_the_reference": bool(np.array_equal(found, result)),
+        }  # fmt: skip
+    return line
 
 
 def multi_gpu_section(torch, dist, ctd, tree, device, rank, world, n_points, steps, tolerance):
@@ -838,7 +853,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_metrics(torch, tree, dev_points, n_points, peak)
         if not args.no_cpu_baseline:
-            secondary.append(c1_reference_line())
+            secondary.append(c1_reference_line(torch))
 
     # ---- multi-GPU: strong scaling, sharded variable-length calls, parity --------------------------------------------
     strong = multi = parity_multi = None
