@@ -178,10 +178,10 @@ int ct_locate_faces(const ct_tree *tree, const double *vertices, int64_t n_verte
  * geometry_utils.sort_intersections_by_edge (geometry_utils.py:564-574).
  * Payload per pair: 4 doubles ((cx, cy), (dx, dy)). */
 int ct_intersect_edges(const ct_tree *tree, const double *edges, int64_t n, int32_t mem, ct_result **out);
-/* Capacity of the hit log of ct_intersect_edges, in hits per query segment (default 16; also CELLTREE_HIT_LOG).
- * The clip of every candidate cell is computed once: hits are counted and logged, then moved to their place after
- * the scan of the counts; if a batch produces more hits than the log holds, a second traversal writes the pairs
- * instead (0 = always).  An execution detail: results are unaffected. */
+/* Slots per query segment in the hit log of ct_intersect_edges (default and maximum 32; also CELLTREE_HIT_LOG; negative:
+ * back to the default).  The clip of every candidate cell is computed once: hits are counted and kept in their segment's
+ * slots, then moved to their place after the scan of the counts; a segment with more hits than slots takes a second
+ * traversal instead (0 = every segment).  An execution detail: results are unaffected. */
 int ct_set_hit_log(int64_t hits_per_query);
 
 int64_t ct_result_size(const ct_result *result);

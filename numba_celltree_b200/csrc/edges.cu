@@ -1,6 +1,6 @@
-// edges.cu -- ct_intersect_edges: warp-cooperative traversal of the query segments that counts and logs the hits
-// (Cohen-Sutherland + Cyrus-Beck against faces, segment/segment against a network), scan, and the placement of
-// every hit at its rank by (t, emission ordinal) within its segment's range.
+// edges.cu -- ct_intersect_edges: warp-cooperative traversal of the query segments that counts the hits and keeps them in
+// per-segment slots (Cohen-Sutherland + Cyrus-Beck against faces, segment/segment against a network), scan, and the
+// placement of every hit at its rank by (t, emission ordinal) within its segment's range.
 #include "hitlog.cuh"
 #include "morton.cuh"
 #include "traverse.cuh"
@@ -17,15 +17,15 @@ namespace ct {
 //   * whenever the queue holds 32 candidates (or the walks are over), the 32 lanes take one candidate each, whoever
 //     pushed it, and run the cheap half of the test (Cohen-Sutherland against the cell's box); the survivors go onto a
 //     second queue, and whenever THAT holds 32 the lanes run the expensive half (Cyrus-Beck against the polygon) on one
-//     survivor each; a hit is appended to the log (hitlog.cuh) with the segment, the candidate's ordinal, the cell and
-//     the clipped points, and counted for its segment.
-// After the scan of the counts, k_place_sources notes for every hit a slot of its segment's range, and k_rank_and_move
-// gives every hit its rank by (t, ordinal) among its segment's hits and moves it from the log to that place: the
-// reference's stable sort by t of the hits in emission order (geometry_utils.py:564-574), since the ordinal grows with the
-// emission order.  Handing the lanes of a warp further segments as they finish (a share of 64 .. 256 segments per warp)
-// was measured and lost: C4 call 47.5 ms with 32 segments per warp, 49.0 / 49.9 / 52.9 ms with 64 / 128 / 256.
-// If the log overflows, the second traversal (one thread per segment, k_locate_edges_fill) writes the pairs in emission
-// order and k_sort_edge_ranges sorts every range in place.
+//     survivor each; a hit is counted for its segment and kept in the slot of the segment's part of the log (hitlog.cuh)
+//     that the count names, with the candidate's ordinal, the cell and the clipped points.
+// After the scan of the counts, k_rank_slots gives every hit its rank by (t, ordinal) among its segment's hits and moves it
+// from its slot to that place of the segment's range: the reference's stable sort by t of the hits in emission order
+// (geometry_utils.py:564-574), since the ordinal grows with the emission order.  Handing the lanes of a warp further segments
+// as they finish (a share of 64 .. 256 segments per warp) was measured and lost: C4 call 47.5 ms with 32 segments per warp,
+// 49.0 / 49.9 / 52.9 ms with 64 / 128 / 256.  A segment with more hits than slots (32; on C4 a few dozen of 10 M) -- and
+// every segment when there is no log -- takes the second traversal (one thread per segment, k_locate_edges_fill), which
+// writes its pairs in emission order, and k_sort_edge_ranges sorts its range in place.
 constexpr int QUEUE_CAP = 64;  // per warp: a step adds at most 32 candidates, a drain starts at 32
 
 // 120 registers, 4 blocks of 128 threads per SM.  Capping the registers for more resident warps loses: C4 call 40.9 ms
@@ -144,16 +144,18 @@ __global__ void __launch_bounds__(BLOCK, CT_EDGES_MINB) k_edges_cooperative(Tree
                     if constexpr (MAXV == 0) hit = edge_edge_intersect(t, cell2, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d);
                     else hit = edge_face_clip<MAXV>(t, cell2, P2{a2.x, a2.y}, P2{b2.x, b2.y}, c, d);
                     if (hit) {
-                        const int64_t at = hitlog_reserve(log);
-                        if (at < log.capacity) {
-                            log.q[at] = (int32_t)owner_q;
-                            log.k[at] = s_ordinal2[warp][first2 + lane];
-                            log.j[at] = cell2;
-                            double2 *o = reinterpret_cast<double2 *>(log.xy + 4 * at);
-                            o[0] = make_double2(c.x, c.y);
-                            o[1] = make_double2(d.x, d.y);
+                        // counted for its segment; the count it found is the hit's slot in the segment's part of the log
+                        const int nth = atomicAdd(&s_hits[warp][owner2], 1);
+                        if (nth < log.per_query) {
+                            const int64_t at = owner_q * log.per_query + nth;
+                            log.kj[at] = make_int2(s_ordinal2[warp][first2 + lane], cell2);
+                            // the two points as ONE 256-bit store (sm_100: STG.E.ENL2.256): the slots of different segments
+                            // are far apart, so every store instruction is a request of its own at the L2
+                            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(log.xy + 4 * at),
+                                         "l"(__double_as_longlong(c.x)), "l"(__double_as_longlong(c.y)),
+                                         "l"(__double_as_longlong(d.x)), "l"(__double_as_longlong(d.y))
+                                         : "memory");
                         }
-                        atomicAdd(&s_hits[warp][owner2], 1);
                     }
                 }
                 queued2 = first2;
@@ -191,19 +193,6 @@ __global__ void __launch_bounds__(BLOCK, CT_EDGES_MINB) k_edges_cooperative(Tree
     if (valid) counts[q] = s_hits[warp][lane];
 }
 
-// log entry -> some free slot of its segment's range, which only records WHERE in the log the hit is (4 bytes) and whose
-// hit it is (out_i, final): the 40 remaining bytes of the hit are moved once, by k_rank_and_move, straight to their place
-__global__ void __launch_bounds__(256) k_place_sources(HitLog log, int64_t entries, const int64_t *__restrict__ offsets,
-                                                       int32_t *__restrict__ filled, uint32_t *__restrict__ source,
-                                                       int32_t *__restrict__ out_i) {
-    int64_t at = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (at >= entries) return;
-    const int32_t q = __ldcs(log.q + at);
-    const int64_t to = offsets[q] + atomicAdd(filled + q, 1);
-    source[to] = (uint32_t)at;
-    out_i[to] = q;
-}
-
 // (x, ox) before (y, oy): smaller t first, NaN after every number, ties and NaNs by emission ordinal -- the order
 // np.lexsort((t, edge)) gives the hits of one edge that arrive in emission order (geometry_utils.py:564-574)
 CT_DEV bool hit_before(double x, int ox, double y, int oy) {
@@ -212,39 +201,61 @@ CT_DEV bool hit_before(double x, int ox, double y, int oy) {
     return ox < oy;
 }
 
-// One thread per hit (slot m of the result): its rank among its segment's hits under hit_before -- a strict total
-// order, the ordinals of a segment's hits being distinct -- is its position in the segment's range; the hit goes there
-// straight from the log.  A segment with k hits costs k * (k - 1) key evaluations (k = 8.65 on average on C4) spread over
-// k neighbouring threads; the keys of the other hits come through L1 (the neighbours read the same log entries).
-__global__ void __launch_bounds__(256) k_rank_and_move(HitLog log, const double *__restrict__ edges, int64_t total,
-                                                       const int64_t *__restrict__ offsets, const uint32_t *__restrict__ source,
-                                                       const int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
-                                                       double *__restrict__ out_xy) {
-    const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (m >= total) return;
-    const int64_t q = out_i[m];
-    const int64_t lo = offsets[q], hi = offsets[q + 1];
-    const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
-    const double2 a = __ldg(e), b = __ldg(e + 1);
-    const double abx = b.x - a.x, aby = b.y - a.y;
+// One warp per 32 consecutive segments, one segment per iteration, one LANE PER SLOT: the segment's logged hits are read in
+// one coalesced sweep of its part of the log, every lane computes the key t = (c - a) . (b - a) of its hit, the keys go
+// round the warp by shuffles, and a hit's rank among them under hit_before -- a strict total order, the ordinals of a
+// segment's hits being distinct -- is its position in the segment's range of the result, where the lane writes it (the range is
+// contiguous: the warp's stores fall into the same few lines).  A thread per segment walking its own slots was 8.0 ms on C4:
+// every one of its accesses is a 32-byte request of its own, and the L2 takes those at 90 G/s.  Segments with more hits than
+// slots are listed for the second traversal.
+static_assert(HIT_SLOTS_MAX <= 32, "a lane per slot");
+__global__ void __launch_bounds__(256) k_rank_slots(HitLog log, const double *__restrict__ edges, int64_t n,
+                                                    const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+                                                    int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
+                                                    double *__restrict__ out_xy, int32_t *__restrict__ redo_count,
+                                                    int32_t *__restrict__ redo_list) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t q0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5) << 5;
+    if (q0 >= n) return;
+    const int my_count = q0 + lane < n ? counts[q0 + lane] : 0;
+    const int64_t my_lo = q0 + lane < n ? offsets[q0 + lane] : 0;
+    if (my_count > log.per_query) redo_list[atomicAdd(redo_count, 1)] = (int32_t)(q0 + lane);
     const double2 *log_xy = reinterpret_cast<const double2 *>(log.xy);
-    const int64_t at = source[m];
-    const double2 c = log_xy[2 * at], d = log_xy[2 * at + 1];
-    const double tm = (c.x - a.x) * abx + (c.y - a.y) * aby;  // t = (c - a) . (b - a)
-    const int om = log.k[at];
-    int64_t rank = 0;
-    for (int64_t m2 = lo; m2 < hi; m2++) {
-        if (m2 == m) continue;
-        const int64_t at2 = source[m2];
-        const double2 c2 = log_xy[2 * at2];
-        const double t2 = (c2.x - a.x) * abx + (c2.y - a.y) * aby;
-        rank += hit_before(t2, log.k[at2], tm, om) ? 1 : 0;
+    // (requesting the next segment's slots before the shuffles of the current one: 3.6 against 3.3 ms -- not latency)
+    for (int i = 0; i < 32; i++) {
+        const int k = __shfl_sync(FULL, my_count, i);
+        const int64_t lo = __shfl_sync(FULL, my_lo, i);
+        if (k == 0 || k > log.per_query) continue;  // the same for all lanes
+        const int64_t q = q0 + i;
+        const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
+        const double2 a = __ldg(e), b = __ldg(e + 1);  // one address for the warp
+        const double abx = b.x - a.x, aby = b.y - a.y;
+        const bool have = lane < k;
+        const int64_t at = q * log.per_query + lane;
+        int2 kj = make_int2(0, 0);
+        double2 c = make_double2(0.0, 0.0), d = c;
+        if (have) {
+            kj = log.kj[at];
+            c = log_xy[2 * at];
+            d = log_xy[2 * at + 1];
+        }
+        const double key = (c.x - a.x) * abx + (c.y - a.y) * aby;
+        int rank = 0;
+        for (int s = 0; s < k; s++) {
+            const double other = __shfl_sync(FULL, key, s);
+            const int other_ordinal = __shfl_sync(FULL, kj.x, s);
+            rank += (s != lane && hit_before(other, other_ordinal, key, kj.x)) ? 1 : 0;
+        }
+        if (have) {
+            const int64_t to = lo + rank;
+            out_i[to] = (int32_t)q;
+            out_j[to] = kj.y;
+            double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
+            o[0] = c;
+            o[1] = d;
+        }
     }
-    const int64_t to = lo + rank;
-    out_j[to] = log.j[at];
-    double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
-    o[0] = c;
-    o[1] = d;
 }
 
 // the second traversal, one thread per segment: pairs in emission order (their ordinal is their rank)
@@ -264,10 +275,12 @@ template <int MAXV, bool DEEP>
 __global__ void __launch_bounds__(BLOCK) k_locate_edges_fill(TreeView t, const double *__restrict__ edges, int64_t n,
                                                              const int64_t *__restrict__ offsets, int32_t *__restrict__ out_i,
                                                              int32_t *__restrict__ out_j, double *__restrict__ out_xy,
-                                                             int32_t *__restrict__ ordinal, const uint32_t *__restrict__ perm) {
+                                                             int32_t *__restrict__ ordinal, const uint32_t *__restrict__ perm,
+                                                             const int32_t *__restrict__ list) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (q >= n) return;
-    if (perm) q = __ldg(perm + q);  // execution order only
+    if (q >= n) return;  // n = entries of `list` (the segments whose hits did not fit the log) if there is one
+    if (list) q = __ldg(list + q);
+    else if (perm) q = __ldg(perm + q);  // execution order only
     const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
     double2 a2 = __ldg(e), b2 = __ldg(e + 1);
     P2 a{a2.x, a2.y}, b{b2.x, b2.y};
@@ -287,9 +300,11 @@ __global__ void __launch_bounds__(BLOCK) k_locate_edges_fill(TreeView t, const d
 // The range arrives in no particular order with the emission ordinal of every hit: sorting by (t, ordinal) is the same.
 __global__ void __launch_bounds__(BLOCK) k_sort_edge_ranges(const double *__restrict__ edges, int64_t n,
                                                             const int64_t *__restrict__ offsets, int32_t *__restrict__ out_j,
-                                                            double *__restrict__ out_xy, int32_t *__restrict__ ordinal) {
+                                                            double *__restrict__ out_xy, int32_t *__restrict__ ordinal,
+                                                            const int32_t *__restrict__ list) {
     int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (q >= n) return;
+    if (q >= n) return;  // n = entries of `list` if there is one (the other segments came sorted out of the log)
+    if (list) q = __ldg(list + q);
     int64_t lo = offsets[q], hi = offsets[q + 1];
     if (hi - lo < 2) return;
     const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
@@ -327,7 +342,7 @@ static int64_t g_hit_log = -1;
 int64_t hit_log_per_query() {
     if (g_hit_log < 0) {
         const char *e = getenv("CELLTREE_HIT_LOG");
-        g_hit_log = e ? atoll(e) : 16;
+        g_hit_log = e ? atoll(e) : HIT_SLOTS_MAX;
     }
     return g_hit_log;
 }
@@ -343,13 +358,13 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     int64_t total = 0;
     MortonOrder order;
     CT_CHECK(order.build<KEY_EDGE>(tree, d_edges, n, s));
-    HitLogBuffers buffers;
-    CT_CHECK(buffers.alloc(n, hit_log_per_query(), true, s));
-    const HitLog &log = buffers.log;
     DeepScope deep;
     CT_CHECK(deep.init(tree, n, s));
     v.deep = deep.view;
     const bool deep_tree = deep.view.slab != nullptr;
+    HitLogBuffers buffers;
+    CT_CHECK(buffers.alloc(n, deep_tree ? 0 : hit_log_per_query(), s));
+    const HitLog &log = buffers.log;
     if (n > 0) {
         CT_CHECK(deep.next_launch());
         if (deep_tree) k_locate_edges_count_deep<MAXV><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, counts.p, order.perm);
@@ -363,28 +378,34 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
     r->size = total;
     r->width = 4;
     if (n > 0 && total > 0) {
-        if (!deep_tree && total <= log.capacity) {
-            // every hit is in the log: note where (one slot per hit in its segment's range), then rank and move
-            Scratch<uint32_t> source;
-            CT_CHECK(source.alloc(total, s));
-            CT_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)n, s));  // reused as per-segment fill counters
-            k_place_sources<<<grid_for(total, 256), 256, 0, s>>>(log, total, offsets.p, counts.p, source.p, r->i);
+        // the segments whose hits are all in the log are ranked and written from there; the others (all of them without a
+        // log) are listed and take the second traversal: pairs in emission order, then the per-segment insertion sort
+        int32_t redo = -1;  // -1: every segment
+        Scratch<int32_t> redo_list, redo_count;
+        if (log.per_query > 0) {
+            CT_CHECK(redo_list.alloc(n, s));
+            CT_CHECK(redo_count.alloc(1, s));
+            CT_CUDA(cudaMemsetAsync(redo_count.p, 0, sizeof(int32_t), s));
+            k_rank_slots<<<grid_for(n, 256), 256, 0, s>>>(log, d_edges, n, counts.p, offsets.p, r->i, r->j, r->payload, redo_count.p,
+                                                          redo_list.p);
             CT_LAUNCH_CHECK();
-            k_rank_and_move<<<grid_for(total, 256), 256, 0, s>>>(log, d_edges, total, offsets.p, source.p, r->i, r->j, r->payload);
-            CT_LAUNCH_CHECK();
-        } else {
-            // the log overflowed: second traversal, pairs in emission order, then the per-segment insertion sort
+            CT_CUDA(cudaMemcpyAsync(&redo, redo_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CT_CUDA(cudaStreamSynchronize(s));
+        }
+        if (redo != 0) {
+            const int64_t n_redo = redo < 0 ? n : redo;
+            const int32_t *list = redo < 0 ? nullptr : redo_list.p;
             Scratch<int32_t> ordinal;
             CT_CHECK(ordinal.alloc(total, s));
             CT_CHECK(deep.next_launch());
             if (deep_tree)
-                k_locate_edges_fill<MAXV, true><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
-                                                                                    ordinal.p, order.perm);
+                k_locate_edges_fill<MAXV, true><<<grid_for(n_redo, BLOCK), BLOCK, 0, s>>>(v, d_edges, n_redo, offsets.p, r->i, r->j,
+                                                                                         r->payload, ordinal.p, order.perm, list);
             else
-                k_locate_edges_fill<MAXV, false><<<grid_for(n, BLOCK), BLOCK, 0, s>>>(v, d_edges, n, offsets.p, r->i, r->j, r->payload,
-                                                                                     ordinal.p, order.perm);
+                k_locate_edges_fill<MAXV, false><<<grid_for(n_redo, BLOCK), BLOCK, 0, s>>>(v, d_edges, n_redo, offsets.p, r->i, r->j,
+                                                                                          r->payload, ordinal.p, order.perm, list);
             CT_LAUNCH_CHECK();
-            k_sort_edge_ranges<<<grid_for(n, BLOCK), BLOCK, 0, s>>>(d_edges, n, offsets.p, r->j, r->payload, ordinal.p);
+            k_sort_edge_ranges<<<grid_for(n_redo, BLOCK), BLOCK, 0, s>>>(d_edges, n_redo, offsets.p, r->j, r->payload, ordinal.p, list);
             CT_LAUNCH_CHECK();
         }
     }
@@ -396,7 +417,7 @@ static int run_edges(const ct_tree *tree, const double *d_edges, int64_t n, ct_r
 using namespace ct;
 
 extern "C" int ct_set_hit_log(int64_t hits_per_query) {
-    g_hit_log = hits_per_query < 0 ? 16 : hits_per_query;
+    g_hit_log = hits_per_query < 0 ? HIT_SLOTS_MAX : hits_per_query;
     return CT_OK;
 }
 
