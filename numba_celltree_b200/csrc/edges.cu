@@ -201,7 +201,7 @@ CT_DEV bool hit_before(double x, int ox, double y, int oy) {
     return ox < oy;
 }
 
-// One warp per 32 consecutive segments, one segment per iteration, one LANE PER SLOT: the segment's logged hits are read in
+// One warp per 32 consecutive segments, one segment (or two of at most 16 hits) per iteration, one LANE PER SLOT: the segment's logged hits are read in
 // one coalesced sweep of its part of the log, every lane computes the key t = (c - a) . (b - a) of its hit, the keys go
 // round the warp by shuffles, and a hit's rank among them under hit_before -- a strict total order, the ordinals of a
 // segment's hits being distinct -- is its position in the segment's range of the result, where the lane writes it (the range is
@@ -223,29 +223,39 @@ __global__ void __launch_bounds__(256) k_rank_slots(HitLog log, const double *__
     if (my_count > log.per_query) redo_list[atomicAdd(redo_count, 1)] = (int32_t)(q0 + lane);
     const double2 *log_xy = reinterpret_cast<const double2 *>(log.xy);
     // (requesting the next segment's slots before the shuffles of the current one: 3.6 against 3.3 ms -- not latency)
-    for (int i = 0; i < 32; i++) {
-        const int k = __shfl_sync(FULL, my_count, i);
-        const int64_t lo = __shfl_sync(FULL, my_lo, i);
-        if (k == 0 || k > log.per_query) continue;  // the same for all lanes
-        const int64_t q = q0 + i;
-        const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
-        const double2 a = __ldg(e), b = __ldg(e + 1);  // one address for the warp
-        const double abx = b.x - a.x, aby = b.y - a.y;
-        const bool have = lane < k;
-        const int64_t at = q * log.per_query + lane;
+    // `width` lanes per segment: 32, or 16 with segment i in the lower and segment i + 1 in the upper half of the warp
+    auto run = [&](int i, int width) {
+        const int half = width == 16 ? (lane >> 4) : 0;
+        const int sub = width == 16 ? (lane & 15) : lane;
+        const int k = __shfl_sync(FULL, my_count, i + half);
+        const int64_t lo = __shfl_sync(FULL, my_lo, i + half);
+        const bool ok = k > 0 && k <= log.per_query;
+        const int rounds_mine = ok ? k : 0;
+        const int rounds_lower = __shfl_sync(FULL, rounds_mine, 0), rounds_upper = __shfl_sync(FULL, rounds_mine, 16);
+        const int rounds = rounds_lower > rounds_upper ? rounds_lower : rounds_upper;
+        if (rounds == 0) return;  // the same for all lanes
+        const int64_t q = q0 + i + half;
+        const bool have = ok && sub < k;
         int2 kj = make_int2(0, 0);
-        double2 c = make_double2(0.0, 0.0), d = c;
+        double2 a = make_double2(0.0, 0.0), b = a, c = a, d = a;
         if (have) {
+            const double2 *e = reinterpret_cast<const double2 *>(edges) + 2 * q;
+            a = __ldg(e);  // one address per segment
+            b = __ldg(e + 1);
+            const int64_t at = q * log.per_query + sub;
             kj = log.kj[at];
             c = log_xy[2 * at];
             d = log_xy[2 * at + 1];
         }
+        const double abx = b.x - a.x, aby = b.y - a.y;
         const double key = (c.x - a.x) * abx + (c.y - a.y) * aby;
+        const int first_lane = lane - sub;  // of this lane's segment
         int rank = 0;
-        for (int s = 0; s < k; s++) {
-            const double other = __shfl_sync(FULL, key, s);
-            const int other_ordinal = __shfl_sync(FULL, kj.x, s);
-            rank += (s != lane && hit_before(other, other_ordinal, key, kj.x)) ? 1 : 0;
+        for (int s = 0; s < rounds; s++) {
+            const int from = first_lane + (s < width ? s : 0);
+            const double other = __shfl_sync(FULL, key, from);
+            const int other_ordinal = __shfl_sync(FULL, kj.x, from);
+            rank += (s < k && s != sub && hit_before(other, other_ordinal, key, kj.x)) ? 1 : 0;
         }
         if (have) {
             const int64_t to = lo + rank;
@@ -254,6 +264,16 @@ __global__ void __launch_bounds__(256) k_rank_slots(HitLog log, const double *__
             double2 *o = reinterpret_cast<double2 *>(out_xy + 4 * to);
             o[0] = c;
             o[1] = d;
+        }
+    };
+    for (int i = 0; i < 32; i += 2) {
+        const int k0 = __shfl_sync(FULL, my_count, i), k1 = __shfl_sync(FULL, my_count, i + 1);
+        const bool small0 = k0 <= 16 || k0 > log.per_query, small1 = k1 <= 16 || k1 > log.per_query;  // (the latter are skipped)
+        if (small0 && small1) {
+            run(i, 16);  // 95 % of C4's segments have at most 16 hits: two segments per iteration
+        } else {
+            run(i, 32);
+            run(i + 1, 32);
         }
     }
 }
